@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the HAWQ integer forward path on B200 (contract in the task statement / DESIGN.md §Measurement).
+
+  python bench.py --gpus N --steps K --warmup W            one JSON line: images/s of the quantized ResNet forward
+  python bench.py --impl reference ...                     the reference's CPU path (oracle port) on the host cores
+
+A "step" = one forward of the frozen quantized ResNet over one batch of synthetic int8 images per GPU.
+Default workload: ResNet-50 W8A8 (bit_config_resnet50_uniform8), batch 128 per GPU (BASELINE.json configs[2]).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "images/sec ResNet-50 W8A8 & W4A4 @batch128, 1/2/4/8xB200; % int-TC roofline"
+MACS_PER_IMAGE = {"resnet18": 1.8141e9, "resnet50": 3.8580e9, "resnet101": 7.57e9}
+INT8_TC_PEAK_OPS = 4.5e15        # nominal dense int8 tcgen05 peak (op/s); reported for context only
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arch", default="resnet50")
+    ap.add_argument("--scheme", default="uniform8")
+    ap.add_argument("--batch", type=int, default=128, help="images per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--residual-bits", type=int, default=16)
+    ap.add_argument("--detail", default="", help="write per-layer timings to this JSON file")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured", d
+    return 6650.0, "fallback", {}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [v.strip() for v in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_forward_rate(arch, scheme, batch, steps, warmup):
+    """The reference's fake-quant forward (oracle/fakequant.py restatement, pinned bit-exact to the unmodified
+    reference) on all host cores."""
+    from oracle import fakequant as fq
+    from hawq_b200.bit_config import get_bit_config
+    from hawq_b200.synthetic import synthetic_batch, synthetic_float_resnet
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    net = synthetic_float_resnet(arch, 0)
+    m = fq.FakeQuantResNet(arch, net, get_bit_config(arch, scheme))
+    m(synthetic_batch(4, 0))
+    m.freeze()
+    x = synthetic_batch(batch, 1)
+    for _ in range(warmup):
+        m(x)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        m(x)
+        ts.append(time.perf_counter() - t0)
+    return batch / (sum(ts) / len(ts)), threads, sum(ts) / len(ts)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(a.steps, 10))
+    warm = max(1, min(a.warmup, 2))
+    ips, threads, sec = cpu_forward_rate(a.arch, a.scheme, a.cpu_batch, steps, warm)
+    line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": a.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32 emulating int8/int4 (reference fake-quant)", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "%s_%s_b%d" % (a.arch, a.scheme, a.batch), "arch": a.arch, "bit_config": a.scheme,
+                       "batch_per_gpu": a.batch, "input": "synthetic 224x224"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": "%d steps of a %d-image batch through oracle/fakequant.py (torch CPU restatement of the "
+                                       "reference forward, bit-exact vs the unmodified reference in the build container)" % (steps, a.cpu_batch)},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import torch.distributed as dist
+    import hawq_b200 as hb
+    from hawq_b200 import ops
+    from hawq_b200.build import build_library
+    from hawq_b200.synthetic import synthetic_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    build_library()
+
+    B = a.batch
+    q = hb.build_synthetic_qresnet(a.arch, a.scheme, calib_batch=4, calib_seed=0)
+    s_in = float(q.quant_input.current_scale())
+    # synthetic int8 images: POOL different batches per rank so consecutive steps never see the same input
+    POOL = 4
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_pool = [torch.clamp(torch.round(torch.randn(B, 224, 224, 3, generator=g) / s_in), -128, 127).to(torch.int8).pin_memory()
+                 for _ in range(POOL)]
+    dev_pool = [t.to(dev) for t in host_pool]
+    eng = hb.compile_model(q, dev_pool[0], residual_bits=a.residual_bits)
+    gathered = None
+
+    def step(i, src):
+        out = eng.run_async(src[i % POOL])
+        if world > 1:
+            return hb.all_gather_logits(out)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ("value")
+    for i in range(max(a.warmup, 3)):
+        step(i, dev_pool)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        step(i, dev_pool)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    flag = int(eng.flag.item())
+    # ---- end-to-end through the public call with host buffers ("e2e")
+    def e2e_step(i):
+        out = eng(host_pool[i % POOL])                 # H2D of the int8 batch, forward, overflow check (+ exact fallback)
+        if world > 1:
+            out = hb.all_gather_logits(out)
+        return out.to("cpu", non_blocking=False)       # D2H of the logits
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(a.steps):
+        res = e2e_step(i)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clk = clocks.stop() if clocks is not None else None
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline leg: per-launch CUDA-event timing of an eager (un-graphed) pass, same stream, same buffers
+    roof, detail = None, None
+    if rank == 0 and not a.no_roofline:
+        roof, detail = roofline_leg(hb, ops, q, dev_pool, a)
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        ips, threads, sec = cpu_forward_rate(a.arch, a.scheme, a.cpu_batch, 3, 1)
+        cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": "3 forwards of a %d-image batch (%.2f s each) through oracle/fakequant.py, the torch-CPU restatement of the "
+                         "reference's fake-quant forward (the Python reference itself cannot travel to the GPU box)" % (a.cpu_batch, sec)}
+    if rank == 0:
+        total_imgs = B * world * a.steps
+        value = total_imgs / (ms / 1e3)
+        macs = MACS_PER_IMAGE.get(a.arch, 0.0)
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int8" if a.scheme == "uniform8" else ("int4 storage / int8 MMA" if a.scheme == "uniform4" else "mixed int4/int8"),
+                "data": "synthetic",
+                "config": {"workload": "%s_%s_b%d" % (a.arch, a.scheme, B), "arch": a.arch, "bit_config": a.scheme, "batch_per_gpu": B,
+                           "global_batch": B * world, "input": "synthetic int8 NHWC 224x224x3, %d rotating batches" % POOL,
+                           "parallelism": "dp%d (batch sharded, logits all-gather)" % world if world > 1 else "single GPU",
+                           "l2": "per-step working set (%.1f GB of activations) exceeds the 126 MB L2; inputs rotate" % (detail["act_bytes"] / 1e9 if detail else 0.0),
+                           "residual_stream": "uint%d" % a.residual_bits if a.residual_bits == 16 else "int32", "cuda_graph": True,
+                           "overflow_flag_seen": bool(flag & 1)},
+                "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(host_pool[0].numel()),
+                        "d2h_bytes_per_step": int(B * world * 1000 * 4 + 4), "ms_per_step": ms_e2e / a.steps,
+                        "int32_fallbacks": eng.fallbacks},
+                "gpu_launches": eng.gpu_launches * a.steps,
+                "clocks": clk,
+                "tensor": {"achieved_tops": 2 * macs * value / 1e12, "nominal_int8_peak_tops": INT8_TC_PEAK_OPS / 1e12,
+                           "frac_of_nominal": 2 * macs * value / INT8_TC_PEAK_OPS},
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+        if a.detail and detail is not None:
+            with open(a.detail, "w") as f:
+                json.dump(detail, f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_leg(hb, ops, q, dev_pool, a):
+    """Eager pass with a CUDA event pair around every launch (torch current stream = the launching stream)."""
+    from hawq_b200 import qtensor
+    from hawq_b200.qtensor import IntActivation, Node
+    peak, which, _ = measured_peaks()
+    reps = 5
+    rows = {}
+    for r in range(reps + 1):
+        ops.timer = [] if r > 0 else None
+        qtensor.config.residual_bits = a.residual_bits
+        x = dev_pool[r % len(dev_pool)]
+        n, h, w, c = x.shape
+        with torch.no_grad():
+            q(IntActivation(Node("int", (n, c, h, w), data=x.view(-1), bits=8, signed=True), x.device))
+        qtensor.config.residual_bits = 32
+        torch.cuda.synchronize()
+        if r > 0:
+            for i, (name, info, e0, e1) in enumerate(ops.timer):
+                rows.setdefault(i, {"kernel": name, "macs": info[0], "bytes": info[1], "ms": []})["ms"].append(e0.elapsed_time(e1))
+    ops.timer = None
+    layers = []
+    agg = {}
+    for i in sorted(rows):
+        r = rows[i]
+        ms = statistics.median(r["ms"])
+        layers.append({"i": i, "kernel": r["kernel"], "ms": ms, "macs": r["macs"], "bytes": r["bytes"],
+                       "GBps": r["bytes"] / ms / 1e6, "TOPS": 2 * r["macs"] / ms / 1e9})
+        g = agg.setdefault(r["kernel"], {"ms": 0.0, "bytes": 0, "macs": 0, "launches": 0})
+        g["ms"] += ms; g["bytes"] += r["bytes"]; g["macs"] += r["macs"]; g["launches"] += 1
+    total_ms = sum(g["ms"] for g in agg.values())
+    top = max(agg, key=lambda k: agg[k]["ms"])
+    t = agg[top]
+    achieved = t["bytes"] / (t["ms"] / 1e3) / 1e9
+    roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % which if which == "measured" else "fallback 6650 GB/s",
+            "traffic": None, "launches_per_step": t["launches"], "share_of_step": t["ms"] / total_ms,
+            "algorithmic_bytes_per_step": t["bytes"], "avg_launch_ms": t["ms"] / t["launches"],
+            "tensor_tops": 2 * t["macs"] / (t["ms"] / 1e3) / 1e12,
+            "note": "all %d %s launches of one step: sum of algorithmic bytes / sum of CUDA-event durations (eager pass)" % (t["launches"], top)}
+    detail = {"layers": layers, "by_kernel": agg, "act_bytes": sum(g["bytes"] for g in agg.values()), "eager_step_ms": total_ms}
+    return roof, detail
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

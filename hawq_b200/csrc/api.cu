@@ -1,0 +1,355 @@
+// C ABI of libhawq_b200.so (see include/hawq_b200.h).  Argument validation + kernel launches; no allocation,
+// no synchronisation on the data path (CUDA-graph safe).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "conv_igemm.cuh"
+#include "elementwise.cuh"
+#include "stem.cuh"
+
+using namespace hawq;
+
+struct hawq_handle {
+  int device;
+  int sm_count;
+  int32_t* status;  // device status word (owned)
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) return fail(HAWQ_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+static int launch_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(HAWQ_ERR_CUDA, "%s launch: %s", what, cudaGetErrorString(e));
+  return HAWQ_OK;
+}
+
+static int grid_for(long long work_items, int sm_count) {
+  long long blocks = (work_items + 255) / 256;
+  const long long cap = (long long)sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+template <int BN, bool A4>
+static int set_conv_attr() {
+  CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN, A4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ConvSmem<BN, A4>::TOTAL));
+  return HAWQ_OK;
+}
+
+extern "C" {
+
+int hawq_abi_version(void) { return HAWQ_ABI_VERSION; }
+const char* hawq_last_error(void) { return g_err; }
+
+int hawq_create(int device, hawq_handle** out) {
+  if (!out) return fail(HAWQ_ERR_BAD_ARG, "hawq_create: out is null");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_create: device sm_%d%d is not Blackwell sm_100", prop.major, prop.minor);
+  hawq_handle* h = new hawq_handle();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->status = nullptr;
+  CUDA_TRY(cudaMalloc(&h->status, sizeof(int32_t)));
+  CUDA_TRY(cudaMemset(h->status, 0, sizeof(int32_t)));
+  int rc;
+  if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
+      (rc = set_conv_attr<64, true>()))
+    return rc;
+  *out = h;
+  return HAWQ_OK;
+}
+
+int hawq_destroy(hawq_handle* h) {
+  if (!h) return HAWQ_OK;
+  cudaFree(h->status);
+  delete h;
+  return HAWQ_OK;
+}
+
+int hawq_sm_count(const hawq_handle* h) { return h ? h->sm_count : 0; }
+
+int hawq_reset_status(hawq_handle* h, void* stream) {
+  if (!h) return fail(HAWQ_ERR_BAD_ARG, "null handle");
+  CUDA_TRY(cudaMemsetAsync(h->status, 0, sizeof(int32_t), (cudaStream_t)stream));
+  return HAWQ_OK;
+}
+
+int hawq_get_status(hawq_handle* h, void* stream, int32_t* host_flags) {
+  if (!h || !host_flags) return fail(HAWQ_ERR_BAD_ARG, "null argument");
+  CUDA_TRY(cudaMemcpyAsync(host_flags, h->status, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return HAWQ_OK;
+}
+
+int hawq_copy_status(hawq_handle* h, int32_t* dst, void* stream) {
+  if (!h || !dst) return fail(HAWQ_ERR_BAD_ARG, "null argument");
+  CUDA_TRY(cudaMemcpyAsync(dst, h->status, sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return HAWQ_OK;
+}
+
+static int check_me(uint32_t m, int e, const char* what) {
+  if (e < 1 || e > 62 || m > 0x80000000u) return fail(HAWQ_ERR_BAD_ARG, "%s: dyadic pair out of range (m=%u e=%d)", what, m, e);
+  return HAWQ_OK;
+}
+
+int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x, const int8_t* w,
+                const hawq_chan* chan, const void* res, const hawq_chan* res_chan, const float* fscale, void* out,
+                void* out_low, void* stream) {
+  if (!h || !d || !ep || !x || !w || !chan) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: null argument");
+  if (d->N < 1 || d->H < 1 || d->W < 1 || d->kh < 1 || d->kw < 1 || d->stride < 1 || d->pad < 0)
+    return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: bad geometry");
+  if (d->a_bits != 8 && d->a_bits != 4) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d: a_bits must be 4 or 8");
+  if (d->Cin % 64 != 0 || d->Cout % 64 != 0)
+    return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d: Cin (%d) and Cout (%d) must be multiples of 64", d->Cin, d->Cout);
+  const int Ho = (d->H + 2 * d->pad - d->kh) / d->stride + 1;
+  const int Wo = (d->W + 2 * d->pad - d->kw) / d->stride + 1;
+  if (Ho < 1 || Wo < 1) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: empty output");
+  const long long M = (long long)d->N * Ho * Wo;
+  if (M > 0x7fffff00ll || (long long)d->N * d->H * d->W > 0x7fffff00ll) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d: too many pixels");
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const uint8_t*)x; p.w = w; p.chan = chan; p.res = res; p.res_chan = res_chan; p.fscale = fscale;
+  p.out = out; p.out_low = out_low; p.status = h->status;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.KH = d->kh; p.KW = d->kw;
+  p.stride = d->stride; p.pad = d->pad; p.Ho = Ho; p.Wo = Wo; p.M = (int)M; p.K = d->kh * d->kw * d->Cin;
+  p.cin_chunks = d->Cin / 64;
+  p.x_pix_bytes = d->Cin * d->a_bits / 8;
+  p.mode = ep->mode; p.relu = ep->relu; p.out_bits = ep->out_bits; p.lo = ep->clamp_lo; p.hi = ep->clamp_hi;
+  p.res_kind = ep->res_kind; p.res_bits = ep->res_bits; p.res_m = ep->res_m; p.res_e = ep->res_e;
+  p.y_bits = ep->y_bits; p.low_bits = ep->low_bits; p.low_m = ep->low_m; p.low_e = ep->low_e;
+  p.low_lo = ep->low_lo; p.low_hi = ep->low_hi; p.cout_store = ep->cout_store;
+
+  switch (ep->mode) {
+    case HAWQ_EPI_REQUANT:
+      if (!out) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: REQUANT needs out");
+      if (ep->out_bits != 4 && ep->out_bits != 8 && ep->out_bits != 16 && ep->out_bits != 32)
+        return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: out_bits must be 4/8/16/32");
+      if (ep->clamp_lo > ep->clamp_hi) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: empty clamp range");
+      break;
+    case HAWQ_EPI_RESIDUAL:
+      if (!res) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: RESIDUAL needs res");
+      if (ep->res_kind == 1) {
+        if (!res_chan) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: res_kind 1 needs res_chan");
+      } else if (ep->res_kind == 0) {
+        if (ep->res_bits != 16 && ep->res_bits != 32) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: res_bits must be 16/32");
+        int rc = check_me(ep->res_m, ep->res_e, "hawq_conv2d residual");
+        if (rc) return rc;
+      } else return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: res_kind must be 0/1");
+      if (ep->y_bits != 0 && ep->y_bits != 16 && ep->y_bits != 32) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: y_bits must be 0/16/32");
+      if (ep->y_bits == 16 && !ep->relu) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: uint16 residual stream requires relu");
+      if (ep->y_bits && !out) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: y_bits set but out is null");
+      if (ep->low_bits != 0 && ep->low_bits != 4 && ep->low_bits != 8) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: low_bits must be 0/4/8");
+      if (ep->low_bits) {
+        if (!out_low) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: low_bits set but out_low is null");
+        int rc = check_me(ep->low_m, ep->low_e, "hawq_conv2d low-bit copy");
+        if (rc) return rc;
+      }
+      if (!ep->y_bits && !ep->low_bits) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: RESIDUAL with no output");
+      break;
+    case HAWQ_EPI_RAW_I32:
+      if (!out) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: RAW_I32 needs out");
+      break;
+    case HAWQ_EPI_DEQUANT_F32:
+      if (!out || !fscale) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: DEQUANT_F32 needs out and fscale");
+      if (ep->cout_store < 1 || ep->cout_store > d->Cout) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: bad cout_store");
+      break;
+    default:
+      return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: unknown epilogue mode %d", ep->mode);
+  }
+
+  const bool bn128 = (d->Cout % 128 == 0);
+  const dim3 grid((unsigned)((M + CONV_BM - 1) / CONV_BM), (unsigned)(d->Cout / (bn128 ? 128 : 64)), 1);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d->a_bits == 8) {
+    if (bn128) conv_igemm_kernel<128, false><<<grid, CONV_THREADS, ConvSmem<128, false>::TOTAL, s>>>(p);
+    else conv_igemm_kernel<64, false><<<grid, CONV_THREADS, ConvSmem<64, false>::TOTAL, s>>>(p);
+  } else {
+    if (bn128) conv_igemm_kernel<128, true><<<grid, CONV_THREADS, ConvSmem<128, true>::TOTAL, s>>>(p);
+    else conv_igemm_kernel<64, true><<<grid, CONV_THREADS, ConvSmem<64, true>::TOTAL, s>>>(p);
+  }
+  return launch_check("conv_igemm");
+}
+
+int hawq_conv2d_i8(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x,
+                   const int8_t* w, const hawq_chan* chan, const void* res, const hawq_chan* res_chan,
+                   const float* fscale, void* out, void* out_low, void* stream) {
+  if (d && d->a_bits != 8) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d_i8: a_bits must be 8");
+  return hawq_conv2d(h, d, ep, x, w, chan, res, res_chan, fscale, out, out_low, stream);
+}
+
+int hawq_conv2d_i4(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x,
+                   const int8_t* w, const hawq_chan* chan, const void* res, const hawq_chan* res_chan,
+                   const float* fscale, void* out, void* out_low, void* stream) {
+  if (d && d->a_bits != 4) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d_i4: a_bits must be 4");
+  return hawq_conv2d(h, d, ep, x, w, chan, res, res_chan, fscale, out, out_low, stream);
+}
+
+int hawq_linear_i8(hawq_handle* h, int32_t N, int32_t K, int32_t Cout, int32_t Cout_pad, const int8_t* x,
+                   const int8_t* w, const hawq_chan* chan, const float* fscale, float* out, void* stream) {
+  if (Cout < 1 || Cout > Cout_pad) return fail(HAWQ_ERR_BAD_ARG, "hawq_linear_i8: bad Cout/Cout_pad");
+  hawq_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.N = N; d.H = 1; d.W = 1; d.Cin = K; d.Cout = Cout_pad; d.kh = 1; d.kw = 1; d.stride = 1; d.pad = 0; d.a_bits = 8;
+  hawq_epilogue_desc ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = HAWQ_EPI_DEQUANT_F32;
+  ep.cout_store = Cout;
+  return hawq_conv2d(h, &d, &ep, x, w, chan, nullptr, nullptr, fscale, out, nullptr, stream);
+}
+
+int hawq_stem_conv_i8(hawq_handle* h, int32_t N, int32_t H, int32_t W, const int8_t* x, const int8_t* w,
+                      const hawq_chan* chan, int32_t clamp_lo, int32_t clamp_hi, int16_t* out, void* stream) {
+  if (!h || !x || !w || !chan || !out) return fail(HAWQ_ERR_BAD_ARG, "hawq_stem_conv_i8: null argument");
+  if (N < 1 || H < 7 || W < 7) return fail(HAWQ_ERR_BAD_ARG, "hawq_stem_conv_i8: bad geometry");
+  if (clamp_lo < -32768 || clamp_hi > 32767 || clamp_lo > clamp_hi) return fail(HAWQ_ERR_BAD_ARG, "hawq_stem_conv_i8: clamp must fit int16");
+  if (N > 65535) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_stem_conv_i8: N > 65535");
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const dim3 grid((Wo + STEM_TW - 1) / STEM_TW, (Ho + STEM_TH - 1) / STEM_TH, N);
+  stem_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const uint32_t*)w, chan, N, H, W, Ho, Wo, clamp_lo, clamp_hi, out);
+  return launch_check("stem_conv");
+}
+
+int hawq_maxpool_requant(hawq_handle* h, int32_t N, int32_t H, int32_t W, int32_t C, const int16_t* x, int32_t y_bits,
+                         void* y, int32_t low_bits, uint32_t low_m, int32_t low_e, int32_t low_lo, int32_t low_hi,
+                         void* out_low, void* stream) {
+  if (!h || !x) return fail(HAWQ_ERR_BAD_ARG, "hawq_maxpool_requant: null argument");
+  if (C % 8 != 0) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_maxpool_requant: C %% 8 != 0");
+  if ((y_bits != 0 && y_bits != 16 && y_bits != 32) || (y_bits && !y)) return fail(HAWQ_ERR_BAD_ARG, "hawq_maxpool_requant: bad y");
+  if ((low_bits != 0 && low_bits != 4 && low_bits != 8) || (low_bits && !out_low)) return fail(HAWQ_ERR_BAD_ARG, "hawq_maxpool_requant: bad low");
+  if (low_bits) { int rc = check_me(low_m, low_e, "hawq_maxpool_requant"); if (rc) return rc; }
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  maxpool_requant_kernel<<<grid_for(total, h->sm_count), 256, 0, (cudaStream_t)stream>>>(
+      x, N, H, W, C, Ho, Wo, y_bits, y, low_bits, low_m, low_e, low_lo, low_hi, out_low);
+  return launch_check("maxpool_requant");
+}
+
+int hawq_avgpool_requant(hawq_handle* h, int32_t N, int32_t HW, int32_t C, int32_t x_bits, const void* x, uint32_t m,
+                         int32_t e, int32_t lo, int32_t hi, int8_t* out, void* stream) {
+  if (!h || !x || !out) return fail(HAWQ_ERR_BAD_ARG, "hawq_avgpool_requant: null argument");
+  if (x_bits != 16 && x_bits != 32) return fail(HAWQ_ERR_BAD_ARG, "hawq_avgpool_requant: x_bits must be 16/32");
+  if (lo < -128 || hi > 127) return fail(HAWQ_ERR_BAD_ARG, "hawq_avgpool_requant: clamp must fit int8");
+  int rc = check_me(m, e, "hawq_avgpool_requant");
+  if (rc) return rc;
+  avgpool_requant_kernel<<<grid_for((long long)N * C, h->sm_count), 256, 0, (cudaStream_t)stream>>>(x, N, HW, C, x_bits, m, e, lo, hi, out);
+  return launch_check("avgpool_requant");
+}
+
+int hawq_quantize_input_f32(hawq_handle* h, int32_t N, int32_t C, int32_t H, int32_t W, const float* x, float scale,
+                            int32_t lo, int32_t hi, int8_t* out, void* stream) {
+  if (!h || !x || !out) return fail(HAWQ_ERR_BAD_ARG, "hawq_quantize_input_f32: null argument");
+  if (!(scale > 0.f)) return fail(HAWQ_ERR_BAD_ARG, "hawq_quantize_input_f32: scale must be > 0");
+  if (lo < -128 || hi > 127) return fail(HAWQ_ERR_BAD_ARG, "hawq_quantize_input_f32: clamp must fit int8");
+  const float inv = 1.0f / scale;  // fp32 division, as `1. / scale` in linear_quantize (quant_utils.py:97)
+  quantize_input_kernel<<<grid_for((long long)N * H * W, h->sm_count), 256, 0, (cudaStream_t)stream>>>(x, N, C, H, W, inv, lo, hi, out);
+  return launch_check("quantize_input");
+}
+
+int hawq_requant(hawq_handle* h, int64_t rows, int32_t C, int32_t x_bits, const void* x, const hawq_chan* chan,
+                 int32_t chan_stride, int32_t relu, int32_t out_bits, int32_t lo, int32_t hi, void* out, void* stream) {
+  if (!h || !x || !chan || !out) return fail(HAWQ_ERR_BAD_ARG, "hawq_requant: null argument");
+  if (C % 8 != 0) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_requant: C %% 8 != 0");
+  if (x_bits != 16 && x_bits != 32) return fail(HAWQ_ERR_BAD_ARG, "hawq_requant: x_bits must be 16/32");
+  if (out_bits != 4 && out_bits != 8 && out_bits != 16 && out_bits != 32) return fail(HAWQ_ERR_BAD_ARG, "hawq_requant: out_bits must be 4/8/16/32");
+  if (chan_stride != 0 && chan_stride != 1) return fail(HAWQ_ERR_BAD_ARG, "hawq_requant: chan_stride must be 0/1");
+  requant_kernel<<<grid_for(rows * (C / 8), h->sm_count), 256, 0, (cudaStream_t)stream>>>(x, rows, C, x_bits, chan, chan_stride, relu, out_bits, lo, hi, out);
+  return launch_check("requant");
+}
+
+int hawq_add_requant(hawq_handle* h, int64_t rows, int32_t C, const int32_t* acc, const hawq_chan* chan,
+                     const hawq_epilogue_desc* ep, const void* res, const hawq_chan* res_chan, void* y, void* out_low,
+                     void* stream) {
+  if (!h || !acc || !chan || !ep || !res) return fail(HAWQ_ERR_BAD_ARG, "hawq_add_requant: null argument");
+  if (C % 8 != 0) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_add_requant: C %% 8 != 0");
+  if (ep->res_kind == 1 && !res_chan) return fail(HAWQ_ERR_BAD_ARG, "hawq_add_requant: res_kind 1 needs res_chan");
+  if (ep->res_kind == 0) { int rc = check_me(ep->res_m, ep->res_e, "hawq_add_requant"); if (rc) return rc; }
+  if (ep->y_bits == 16 && !ep->relu) return fail(HAWQ_ERR_BAD_ARG, "hawq_add_requant: uint16 residual stream requires relu");
+  if ((ep->y_bits && !y) || (ep->low_bits && !out_low)) return fail(HAWQ_ERR_BAD_ARG, "hawq_add_requant: missing output");
+  AddRequantParams p;
+  p.acc = acc; p.chan = chan; p.res = res; p.res_chan = res_chan; p.y = y; p.out_low = out_low; p.status = h->status;
+  p.rows = rows; p.C = C; p.relu = ep->relu; p.res_kind = ep->res_kind; p.res_bits = ep->res_bits; p.res_m = ep->res_m;
+  p.res_e = ep->res_e; p.y_bits = ep->y_bits; p.low_bits = ep->low_bits; p.low_m = ep->low_m; p.low_e = ep->low_e;
+  p.low_lo = ep->low_lo; p.low_hi = ep->low_hi;
+  add_requant_kernel<<<grid_for(rows * (C / 8), h->sm_count), 256, 0, (cudaStream_t)stream>>>(p);
+  return launch_check("add_requant");
+}
+
+int hawq_dequant_f32(hawq_handle* h, int32_t N, int32_t H, int32_t W, int32_t C, int32_t x_bits, int32_t x_signed,
+                     const void* x, float scale, float* out_nchw, void* stream) {
+  if (!h || !x || !out_nchw) return fail(HAWQ_ERR_BAD_ARG, "hawq_dequant_f32: null argument");
+  if (x_bits != 4 && x_bits != 8 && x_bits != 16 && x_bits != 32) return fail(HAWQ_ERR_BAD_ARG, "hawq_dequant_f32: bad x_bits");
+  if (x_bits == 4 && C % 8 != 0) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_dequant_f32: packed input needs C %% 8 == 0");
+  dequant_f32_kernel<<<grid_for((long long)N * H * W * C, h->sm_count), 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, x_bits, x_signed, scale, out_nchw);
+  return launch_check("dequant_f32");
+}
+
+int hawq_pack_i4(hawq_handle* h, int64_t n_values, const uint8_t* in, uint8_t* out, void* stream) {
+  if (!h || !in || !out || n_values % 8 != 0) return fail(HAWQ_ERR_BAD_ARG, "hawq_pack_i4: bad argument");
+  pack_i4_kernel<<<grid_for(n_values / 8, h->sm_count), 256, 0, (cudaStream_t)stream>>>(in, n_values / 8, out);
+  return launch_check("pack_i4");
+}
+
+int hawq_unpack_i4(hawq_handle* h, int64_t n_values, const uint8_t* in, uint8_t* out, void* stream) {
+  if (!h || !in || !out || n_values % 8 != 0) return fail(HAWQ_ERR_BAD_ARG, "hawq_unpack_i4: bad argument");
+  unpack_i4_kernel<<<grid_for(n_values / 8, h->sm_count), 256, 0, (cudaStream_t)stream>>>(in, n_values / 8, out);
+  return launch_check("unpack_i4");
+}
+
+// ------------------------------------------------------------------------------------------- host helpers
+int hawq_dyadic(double ratio, uint32_t* m, int32_t* e) {
+  if (!m || !e || !(ratio > 0.0) || !std::isfinite(ratio)) return fail(HAWQ_ERR_BAD_ARG, "hawq_dyadic: ratio must be positive and finite");
+  int ex;
+  const double mant = std::frexp(ratio, &ex);          // mant in [0.5, 1)
+  const double scaled = mant * 2147483648.0;            // exact
+  const double r = std::floor(scaled + 0.5);            // ROUND_HALF_UP for positive values, exact (see oracle/int_ref.py)
+  const int ee = 31 - ex;
+  if (ee < 1) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_dyadic: ratio %g too large (e = %d < 1)", ratio, ee);
+  if (ee > 62) { *m = 0; *e = 1; return HAWQ_OK; }      // |v*m| < 2^62 <= 2^(e-1): always rounds to 0
+  *m = (uint32_t)r;
+  *e = ee;
+  return HAWQ_OK;
+}
+
+int64_t hawq_rhe_requant_host(int32_t v, uint32_t m, int32_t e) { return (int64_t)rhe_requant(v, m, e); }
+
+int hawq_permute_weights_for_i4(int8_t* host_w, int64_t rows_times_taps, int32_t Cin) {
+  if (!host_w || Cin % 32 != 0) return fail(HAWQ_ERR_BAD_ARG, "hawq_permute_weights_for_i4: Cin %% 32 != 0");
+  int8_t tmp[32];
+  for (int64_t r = 0; r < rows_times_taps; ++r) {
+    for (int blk = 0; blk < Cin / 32; ++blk) {
+      int8_t* p = host_w + r * Cin + blk * 32;
+      for (int t = 0; t < 4; ++t)
+        for (int j = 0; j < 4; ++j) {
+          tmp[4 * t + j] = p[8 * t + j];           // MMA k position 4t+j     <- channel 8t+j
+          tmp[16 + 4 * t + j] = p[8 * t + 4 + j];  // MMA k position 16+4t+j  <- channel 8t+4+j
+        }
+      memcpy(p, tmp, 32);
+    }
+  }
+  return HAWQ_OK;
+}
+
+int64_t hawq_workspace_bytes(const hawq_conv_desc*, const hawq_epilogue_desc*) { return 0; }
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// Implicit-GEMM integer convolution with fused HAWQ epilogues (stage-A kernel: IMMA m16n8k32 + cp.async pipeline).
+//
+//   M = N*Ho*Wo output pixels, N = Cout, K = kh*kw*Cin.   A[m,k] gathered on the fly from the NHWC activation
+//   tensor (zero-filled outside the image), B = int8 OHWI weights.  CTA tile 128 x BN x 64 channels, 8 warps
+//   (4 along M x 2 along N), 4-stage cp.async ring, XOR-swizzled shared memory read with ldmatrix.
+//
+//   A4 = true: activations are packed unsigned nibbles (hawq nibble order).  They stay packed in HBM and in shared
+//   memory (half the bytes); each ldmatrix word (8 nibbles) is expanded in registers with AND / SHIFT+AND into the
+//   two int8x4 words of the MMA A fragment.  The weight rows of such layers are K-permuted on the host so that the
+//   expansion needs no shuffles (hawq_permute_weights_for_i4).
+//
+//   Epilogues (hawq_epilogue_mode): REQUANT (case 0 of fixedpoint_fn), RESIDUAL (case 1: dual dyadic requant + add,
+//   optional ReLU, writes the new residual stream and/or the next unit's low-bit activation), RAW_I32, DEQUANT_F32.
+#pragma once
+#include "common.cuh"
+
+namespace hawq {
+
+struct ConvParams {
+  const uint8_t* x;
+  const int8_t* w;
+  const hawq_chan* chan;
+  const void* res;
+  const hawq_chan* res_chan;
+  const float* fscale;
+  void* out;
+  void* out_low;
+  int32_t* status;
+  int N, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo, M, K;
+  int cin_chunks;   // Cin / 64
+  int x_pix_bytes;  // bytes per input pixel (Cin * a_bits / 8)
+  int mode, relu, out_bits, lo, hi;
+  int res_kind, res_bits;
+  uint32_t res_m;
+  int res_e;
+  int y_bits, low_bits;
+  uint32_t low_m;
+  int low_e, low_lo, low_hi;
+  int cout_store;
+};
+
+constexpr int CONV_BM = 128;
+constexpr int CONV_STAGES = 4;
+constexpr int CONV_THREADS = 256;
+
+template <int BN, bool A4>
+struct ConvSmem {
+  static constexpr int A_ROW = A4 ? 32 : 64;  // bytes of one A row per k-tile (64 channels)
+  static constexpr int A_STAGE = CONV_BM * A_ROW;
+  static constexpr int B_STAGE = BN * 64;
+  static constexpr int PIPE = CONV_STAGES * (A_STAGE + B_STAGE);
+  static constexpr int OUT_PITCH = BN + 16;
+  static constexpr int OUT_STAGE = CONV_BM * OUT_PITCH;
+  static constexpr int MAIN = PIPE > OUT_STAGE ? PIPE : OUT_STAGE;
+  static constexpr int TOTAL = MAIN + BN * (int)sizeof(hawq_chan);
+};
+
+// swizzled byte offset of 16-byte chunk `ch` of row `row` (rows of 64 B: 4 chunks; rows of 32 B: 2 chunks)
+template <int ROW_BYTES>
+__device__ __forceinline__ int swz(int row, int ch) {
+  if constexpr (ROW_BYTES == 64) return row * 64 + ((ch ^ ((row >> 1) & 3)) << 4);
+  else return row * 32 + ((ch ^ ((row >> 2) & 1)) << 4);
+}
+
+template <int BN, bool A4>
+__global__ void __launch_bounds__(CONV_THREADS, 2) conv_igemm_kernel(const ConvParams p) {
+  using S = ConvSmem<BN, A4>;
+  constexpr int BM = CONV_BM, STAGES = CONV_STAGES;
+  constexpr int A_ROW = S::A_ROW;
+  constexpr int A_CH = A_ROW / 16;                    // 16-byte chunks per A row: 4 or 2
+  constexpr int A_ROWS_PER_PASS = CONV_THREADS / A_CH;  // 64 or 128
+  constexpr int A_PASSES = BM / A_ROWS_PER_PASS;        // 2 or 1
+  constexpr int B_PASSES = BN / 64;
+  constexpr int WNT = BN / 2;   // warp tile width
+  constexpr int NT = WNT / 8;   // n8 tiles per warp: 8 or 4
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * S::A_STAGE;
+  hawq_chan* sChan = reinterpret_cast<hawq_chan*>(smem + S::MAIN);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  if (tid < BN) sChan[tid] = p.chan[n0 + tid];
+
+  // ---- per-thread gather coordinates for the A rows this thread copies ----
+  const int a_ch = tid % A_CH;
+  int a_hi0[A_PASSES], a_wi0[A_PASSES], a_pix[A_PASSES];
+  bool a_ok[A_PASSES];
+#pragma unroll
+  for (int i = 0; i < A_PASSES; ++i) {
+    const int row = tid / A_CH + i * A_ROWS_PER_PASS;
+    const int m = m0 + row;
+    a_ok[i] = m < p.M;
+    const int mm = a_ok[i] ? m : 0;
+    const int n = mm / (p.Ho * p.Wo);
+    const int r = mm - n * (p.Ho * p.Wo);
+    const int ho = r / p.Wo, wo = r - ho * p.Wo;
+    a_hi0[i] = ho * p.stride - p.pad;
+    a_wi0[i] = wo * p.stride - p.pad;
+    a_pix[i] = n * p.H * p.W;
+  }
+  const int b_ch = tid & 3, b_row = tid >> 2;
+  const int KT = p.KH * p.KW * p.cin_chunks;
+  int ld_c = 0, ld_kw = 0, ld_kh = 0, ld_kt = 0;
+
+  auto load_tile = [&](int stage) {
+    const uint32_t a_base = smem_u32(sA + stage * S::A_STAGE);
+#pragma unroll
+    for (int i = 0; i < A_PASSES; ++i) {
+      const int row = tid / A_CH + i * A_ROWS_PER_PASS;
+      const int hi = a_hi0[i] + ld_kh, wi = a_wi0[i] + ld_kw;
+      const bool v = a_ok[i] && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W;
+      const uint8_t* src = p.x;
+      if (v) src = p.x + (size_t)(a_pix[i] + hi * p.W + wi) * p.x_pix_bytes + ld_c * A_ROW + a_ch * 16;
+      cp_async_16(a_base + swz<A_ROW>(row, a_ch), src, v ? 16 : 0);
+    }
+    const uint32_t b_base = smem_u32(sB + stage * S::B_STAGE);
+#pragma unroll
+    for (int i = 0; i < B_PASSES; ++i) {
+      const int row = b_row + i * 64;
+      const int8_t* src = p.w + (size_t)(n0 + row) * p.K + ld_kt * 64 + b_ch * 16;
+      cp_async_16(b_base + swz<64>(row, b_ch), src, 16);
+    }
+    ++ld_kt;
+    if (++ld_c == p.cin_chunks) {
+      ld_c = 0;
+      if (++ld_kw == p.KW) { ld_kw = 0; ++ld_kh; }
+    }
+  };
+
+  int32_t acc[2][NT][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[mi][ni][k] = 0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_tile(s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (kt + STAGES - 1 < KT) load_tile((kt + STAGES - 1) % STAGES);
+    cp_async_commit();
+
+    const int stage = kt % STAGES;
+    const uint32_t a_base = smem_u32(sA + stage * S::A_STAGE);
+    const uint32_t b_base = smem_u32(sB + stage * S::B_STAGE);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t af[2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int row = wm * 32 + mi * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        if constexpr (!A4) {
+          ldmatrix_x4(af[mi][0], af[mi][1], af[mi][2], af[mi][3], a_base + swz<64>(row, ks * 2 + (lane >> 4)));
+        } else {
+          uint32_t r0, r1;
+          ldmatrix_x2(r0, r1, a_base + swz<32>(row, ks));
+          af[mi][0] = r0 & 0x0F0F0F0Fu;
+          af[mi][1] = r1 & 0x0F0F0F0Fu;
+          af[mi][2] = (r0 >> 4) & 0x0F0F0F0Fu;
+          af[mi][3] = (r1 >> 4) & 0x0F0F0F0Fu;
+        }
+      }
+      uint32_t bf[NT][2];
+#pragma unroll
+      for (int nj = 0; nj < NT / 2; ++nj) {
+        const int row = wn * WNT + nj * 16 + (lane & 7) + (lane >> 4) * 8;
+        ldmatrix_x4(bf[2 * nj][0], bf[2 * nj][1], bf[2 * nj + 1][0], bf[2 * nj + 1][1],
+                    b_base + swz<64>(row, ks * 2 + ((lane >> 3) & 1)));
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) mma_16832<A4>(acc[mi][ni], af[mi], bf[ni]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();   // pipeline buffers are free: reused as the low-bit output staging tile
+
+  // ------------------------------------------------------------------------------------------------ epilogue
+  uint8_t* sOut = smem;
+  const bool stage_low = (p.mode == HAWQ_EPI_REQUANT && p.out_bits <= 8) || (p.mode == HAWQ_EPI_RESIDUAL && p.low_bits != 0);
+  const int stage_bits = (p.mode == HAWQ_EPI_REQUANT) ? p.out_bits : p.low_bits;
+
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int row = wm * 32 + mi * 16 + hf * 8 + g;
+      const int m = m0 + row;
+      const bool ok = m < p.M;
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) {
+        const int col = wn * WNT + ni * 8 + 2 * t;
+        const int4 c0 = *reinterpret_cast<const int4*>(&sChan[col]);
+        const int4 c1 = *reinterpret_cast<const int4*>(&sChan[col + 1]);
+        int32_t v0 = sat_add(acc[mi][ni][hf * 2 + 0], c0.x);
+        int32_t v1 = sat_add(acc[mi][ni][hf * 2 + 1], c1.x);
+        const size_t gidx = (size_t)m * p.Cout + n0 + col;
+        if (p.mode == HAWQ_EPI_REQUANT) {
+          if (p.relu) { v0 = max(v0, 0); v1 = max(v1, 0); }
+          const int32_t q0 = clampi(rhe_requant(v0, (uint32_t)c0.y, c0.z), p.lo, p.hi);
+          const int32_t q1 = clampi(rhe_requant(v1, (uint32_t)c1.y, c1.z), p.lo, p.hi);
+          if (p.out_bits <= 8) {
+            *reinterpret_cast<uint16_t*>(sOut + row * S::OUT_PITCH + col) = (uint16_t)((q0 & 0xFF) | ((q1 & 0xFF) << 8));
+          } else if (ok) {
+            if (p.out_bits == 16) {
+              *reinterpret_cast<uint32_t*>(reinterpret_cast<int16_t*>(p.out) + gidx) =
+                  (uint32_t)(q0 & 0xFFFF) | ((uint32_t)(q1 & 0xFFFF) << 16);
+            } else {
+              *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + gidx) = make_int2(q0, q1);
+            }
+          }
+        } else if (p.mode == HAWQ_EPI_RESIDUAL) {
+          int32_t r0 = 0, r1 = 0;
+          uint32_t rm0 = p.res_m, rm1 = p.res_m;
+          int re0 = p.res_e, re1 = p.res_e;
+          if (ok) {
+            if (p.res_kind == 0 && p.res_bits == 16) {
+              const uint32_t pr = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.res) + gidx);
+              r0 = (int32_t)(pr & 0xFFFFu);
+              r1 = (int32_t)(pr >> 16);
+            } else {
+              const int2 pr = *reinterpret_cast<const int2*>(reinterpret_cast<const int32_t*>(p.res) + gidx);
+              r0 = pr.x;
+              r1 = pr.y;
+            }
+          }
+          if (p.res_kind == 1) {
+            const hawq_chan rc0 = p.res_chan[n0 + col], rc1 = p.res_chan[n0 + col + 1];
+            rm0 = rc0.m; re0 = rc0.e; rm1 = rc1.m; re1 = rc1.e;
+          }
+          int32_t y0 = sat_add(rhe_requant(r0, rm0, re0), rhe_requant(v0, (uint32_t)c0.y, c0.z));
+          int32_t y1 = sat_add(rhe_requant(r1, rm1, re1), rhe_requant(v1, (uint32_t)c1.y, c1.z));
+          if (p.relu) { y0 = max(y0, 0); y1 = max(y1, 0); }
+          if (p.y_bits == 32) {
+            if (ok) *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + gidx) = make_int2(y0, y1);
+          } else if (p.y_bits == 16) {
+            if (ok) {
+              if (y0 > 65535 || y1 > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
+              *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out) + gidx) =
+                  (uint32_t)min(y0, 65535) | ((uint32_t)min(y1, 65535) << 16);
+            }
+          }
+          if (p.low_bits != 0) {
+            const int32_t q0 = clampi(rhe_requant(y0, p.low_m, p.low_e), p.low_lo, p.low_hi);
+            const int32_t q1 = clampi(rhe_requant(y1, p.low_m, p.low_e), p.low_lo, p.low_hi);
+            *reinterpret_cast<uint16_t*>(sOut + row * S::OUT_PITCH + col) = (uint16_t)((q0 & 0xFF) | ((q1 & 0xFF) << 8));
+          }
+        } else if (p.mode == HAWQ_EPI_RAW_I32) {
+          if (ok) *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + gidx) = make_int2(v0, v1);
+        } else {  // HAWQ_EPI_DEQUANT_F32
+          if (ok) {
+            float* o = reinterpret_cast<float*>(p.out) + (size_t)m * p.cout_store;
+            const int c = n0 + col;
+            if (c < p.cout_store) o[c] = __fmul_rn((float)v0, p.fscale[c]);
+            if (c + 1 < p.cout_store) o[c + 1] = __fmul_rn((float)v1, p.fscale[c + 1]);
+          }
+        }
+      }
+    }
+  }
+
+  if (stage_low) {
+    __syncthreads();
+    uint8_t* gout = reinterpret_cast<uint8_t*>(p.mode == HAWQ_EPI_REQUANT ? p.out : p.out_low);
+    if (stage_bits == 8) {
+      constexpr int CPR = BN / 16;
+      for (int id = tid; id < BM * CPR; id += CONV_THREADS) {
+        const int row = id / CPR, j = id % CPR;
+        if (m0 + row < p.M) {
+          const int4 v = *reinterpret_cast<const int4*>(sOut + row * S::OUT_PITCH + j * 16);
+          *reinterpret_cast<int4*>(gout + (size_t)(m0 + row) * p.Cout + n0 + j * 16) = v;
+        }
+      }
+    } else {  // 4-bit: 32 channels -> 16 packed bytes
+      constexpr int CPR = BN / 32;
+      for (int id = tid; id < BM * CPR; id += CONV_THREADS) {
+        const int row = id / CPR, j = id % CPR;
+        if (m0 + row < p.M) {
+          const uint4 a = *reinterpret_cast<const uint4*>(sOut + row * S::OUT_PITCH + j * 32);
+          const uint4 b = *reinterpret_cast<const uint4*>(sOut + row * S::OUT_PITCH + j * 32 + 16);
+          uint4 o;
+          o.x = pack_nibbles8(a.x, a.y);
+          o.y = pack_nibbles8(a.z, a.w);
+          o.z = pack_nibbles8(b.x, b.y);
+          o.w = pack_nibbles8(b.z, b.w);
+          *reinterpret_cast<uint4*>(gout + (((size_t)(m0 + row) * p.Cout + n0 + j * 32) >> 1)) = o;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace hawq

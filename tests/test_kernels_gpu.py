@@ -1,0 +1,228 @@
+"""-m gpu: every CUDA kernel behind the C ABI against the numpy ABI model (tests/abi_model.py -> oracle/int_ref.py)
+on the same seeded buffers.  Integer work: bit-exact, no tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from hawq_b200 import ops
+from hawq_b200._lib import EPI_DEQUANT_F32, EPI_RAW_I32, EPI_REQUANT, EPI_RESIDUAL, HawqError, dyadic
+from tests import abi_model as am
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rng(seed):
+    return np.random.RandomState(seed)
+
+
+def make_chan(r, c, bias_mag=2 ** 16, ratio_lo=1e-4, ratio_hi=0.05):
+    bias = r.randint(-bias_mag, bias_mag, size=c)
+    me = [dyadic(float(np.exp(r.uniform(np.log(ratio_lo), np.log(ratio_hi))))) for _ in range(c)]
+    return ops.make_chan(bias, [m for m, _ in me], [e for _, e in me])
+
+
+def rand_act(r, n_vals, bits, signed=True):
+    if bits == 4:
+        v = r.randint(0, 16, size=n_vals)
+        return torch.from_numpy(am.pack_i4(v))
+    if bits == 8:
+        return torch.from_numpy(r.randint(-128, 128, size=n_vals).astype(np.int8))
+    if bits == 16:
+        return torch.from_numpy(r.randint(0, 40000, size=n_vals).astype(np.uint16).view(np.int16))
+    return torch.from_numpy(r.randint(-40000, 40000, size=n_vals).astype(np.int32))
+
+
+def out_buf(numel, bits):
+    dt = {4: torch.uint8, 8: torch.int8, 16: torch.int16, 32: torch.int32}[bits]
+    return torch.zeros(numel // 2 if bits == 4 else numel, dtype=dt)
+
+
+def run_both(fn_name, cpu_args, out_keys):
+    """cpu_args: dict of kwargs with CPU tensors; out_keys: names of output tensors.  Returns (cpu_outs, gpu_outs)."""
+    gpu_args = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in cpu_args.items()}
+    getattr(am, fn_name)(**cpu_args)
+    getattr(ops, fn_name)(**gpu_args)
+    torch.cuda.synchronize()
+    return [cpu_args[k] for k in out_keys], [gpu_args[k].cpu() for k in out_keys]
+
+
+CONV_GEOMS = [
+    # N, H, W, Cin, Cout, k, stride, pad
+    (2, 8, 8, 64, 64, 1, 1, 0),
+    (3, 7, 7, 64, 128, 3, 1, 1),       # M = 147: ragged last tile
+    (2, 14, 14, 128, 64, 3, 2, 1),
+    (2, 9, 9, 256, 256, 1, 2, 0),
+    (1, 20, 12, 64, 192, 3, 1, 1),     # Cout = 192 -> BN = 64 path with 3 column tiles
+    (5, 6, 6, 128, 128, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("a_bits", [8, 4])
+@pytest.mark.parametrize("geom", CONV_GEOMS)
+def test_conv_requant(geom, a_bits):
+    n, h, w, cin, cout, k, s, p = geom
+    r = rng(sum(v * (i + 3) for i, v in enumerate(geom)) * 8 + a_bits)
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    x = rand_act(r, n * h * w * cin, a_bits)
+    wt = torch.from_numpy(r.randint(-128 if a_bits == 8 else -8, 128 if a_bits == 8 else 8, size=(cout, k, k, cin)).astype(np.int8))
+    if a_bits == 4:
+        ops.permute_weights_for_i4(wt)
+    for out_bits, clamp, relu in [(8, (-128, 127), 1), (4, (0, 15), 1), (16, (-32768, 32767), 0), (32, (-2 ** 31, 2 ** 31 - 1), 0)]:
+        chan = make_chan(r, cout, ratio_lo=1e-5 if out_bits <= 8 else 1e-3)
+        d = ops.conv_desc(n, h, w, cin, cout, k, k, s, p, a_bits)
+        ep = ops.epilogue(EPI_REQUANT, relu=relu, out_bits=out_bits, clamp=clamp)
+        (c_out,), (g_out,) = run_both("conv2d", dict(x=x, desc=d, ep=ep, w=wt, chan=chan, out=out_buf(n * ho * wo * cout, out_bits)), ["out"])
+        assert torch.equal(c_out, g_out), (geom, a_bits, out_bits)
+
+
+@pytest.mark.parametrize("a_bits", [8, 4])
+@pytest.mark.parametrize("geom", CONV_GEOMS[:4])
+def test_conv_residual(geom, a_bits):
+    n, h, w, cin, cout, k, s, p = geom
+    r = rng(sum(v * (i + 5) for i, v in enumerate(geom)) * 8 + a_bits + 1)
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    numel = n * ho * wo * cout
+    x = rand_act(r, n * h * w * cin, a_bits)
+    wt = torch.from_numpy(r.randint(-8, 8, size=(cout, k, k, cin)).astype(np.int8))
+    if a_bits == 4:
+        ops.permute_weights_for_i4(wt)
+    chan = make_chan(r, cout, ratio_lo=1e-2, ratio_hi=0.9)
+    d = ops.conv_desc(n, h, w, cin, cout, k, k, s, p, a_bits)
+    low_me = dyadic(0.004)
+    for res_kind, res_bits, y_bits, low_bits, relu in [(0, 32, 32, 8, 1), (0, 16, 16, 4, 1), (1, 32, 32, 4, 1),
+                                                       (0, 32, 32, 0, 0), (1, 32, 0, 8, 1), (0, 16, 16, 8, 1)]:
+        res = rand_act(r, numel, res_bits if res_kind == 0 else 32)
+        res_chan = make_chan(r, cout, ratio_lo=1e-2, ratio_hi=0.9) if res_kind == 1 else None
+        res_me = dyadic(0.37)
+        ep = ops.epilogue(EPI_RESIDUAL, relu=relu, res_kind=res_kind, res_bits=res_bits, res_me=res_me, y_bits=y_bits,
+                          low_bits=low_bits, low_me=low_me, low_clamp=(0, 15) if low_bits == 4 else (-128, 127))
+        args = dict(x=x, desc=d, ep=ep, w=wt, chan=chan, res=res, res_chan=res_chan,
+                    out=out_buf(numel, y_bits) if y_bits else None, out_low=out_buf(numel, low_bits) if low_bits else None)
+        keys = [k_ for k_ in ("out", "out_low") if args[k_] is not None]
+        c_outs, g_outs = run_both("conv2d", args, keys)
+        for a, b, k_ in zip(c_outs, g_outs, keys):
+            assert torch.equal(a, b), (geom, a_bits, res_kind, res_bits, y_bits, low_bits, k_)
+
+
+def test_residual_overflow_flag():
+    r = rng(5)
+    n, h, w, cin, cout = 1, 4, 4, 64, 64
+    x = rand_act(r, n * h * w * cin, 8)
+    wt = torch.from_numpy(r.randint(-8, 8, size=(cout, 1, 1, cin)).astype(np.int8))
+    chan = make_chan(r, cout, ratio_lo=0.5, ratio_hi=0.9)
+    res = torch.full((n * h * w * cout,), 60000, dtype=torch.int32)
+    d = ops.conv_desc(n, h, w, cin, cout, 1, 1, 1, 0, 8)
+    ep = ops.epilogue(EPI_RESIDUAL, relu=1, res_kind=0, res_bits=32, res_me=dyadic(1.9), y_bits=16)
+    ops.reset_status(0)
+    y = torch.zeros(n * h * w * cout, dtype=torch.int16, device=DEV)
+    ops.conv2d(x.to(DEV), d, ep, wt.to(DEV), chan.to(DEV), res=res.to(DEV), out=y)
+    assert ops.get_status(0) & 1
+    assert int((y.cpu().view(torch.int16).to(torch.int32) & 0xFFFF).max()) == 65535
+    ops.reset_status(0)
+    assert ops.get_status(0) == 0
+
+
+def test_conv_raw_and_dequant():
+    r = rng(9)
+    n, h, w, cin, cout, k, s, p = 2, 6, 6, 128, 128, 1, 2, 0
+    ho = wo = 3
+    x = rand_act(r, n * h * w * cin, 8)
+    wt = torch.from_numpy(r.randint(-128, 128, size=(cout, k, k, cin)).astype(np.int8))
+    chan = make_chan(r, cout)
+    d = ops.conv_desc(n, h, w, cin, cout, k, k, s, p, 8)
+    (c,), (g,) = run_both("conv2d", dict(x=x, desc=d, ep=ops.epilogue(EPI_RAW_I32), w=wt, chan=chan,
+                                         out=out_buf(n * ho * wo * cout, 32)), ["out"])
+    assert torch.equal(c, g)
+    # linear tail: 1000 classes padded to 1024
+    nb, kk, co, cp = 5, 512, 1000, 1024
+    xl = rand_act(r, nb * kk, 8)
+    wl = torch.zeros((cp, kk), dtype=torch.int8)
+    wl[:co] = torch.from_numpy(r.randint(-128, 128, size=(co, kk)).astype(np.int8))
+    chl = make_chan(r, cp)
+    fs = torch.from_numpy(r.uniform(1e-5, 1e-3, size=cp).astype(np.float32))
+    (c,), (g,) = run_both("linear", dict(x=xl, w=wl, chan=chl, fscale=fs, out=torch.zeros((nb, co)), n=nb, k=kk, cout=co, cout_pad=cp), ["out"])
+    assert torch.equal(c, g)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32), (1, 224, 224), (3, 30, 46)])
+def test_stem_and_pool(shape):
+    n, h, w = shape
+    r = rng(n * h + w)
+    x = torch.from_numpy(r.randint(-128, 128, size=n * h * w * 3).astype(np.int8))
+    wt = torch.zeros((64, 7, 8, 4), dtype=torch.int8)
+    wt[:, :, :7, :3] = torch.from_numpy(r.randint(-128, 128, size=(64, 7, 7, 3)).astype(np.int8))
+    chan = make_chan(r, 64, ratio_lo=0.05, ratio_hi=0.8)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    (c16,), (g16,) = run_both("stem_conv", dict(x=x, w=wt, chan=chan, clamp=(-32768, 32767), out=torch.zeros(n * ho * wo * 64, dtype=torch.int16),
+                                                n=n, hh=h, ww=w), ["out"])
+    assert torch.equal(c16, g16)
+    po, qo = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
+    for y_bits, low_bits in [(16, 8), (32, 4), (16, 0), (0, 8)]:
+        args = dict(x=c16, n=n, hh=ho, ww=wo, c=64, y_bits=y_bits, y=out_buf(n * po * qo * 64, y_bits) if y_bits else None,
+                    low_bits=low_bits, low_me=dyadic(0.003), low_clamp=(0, 15) if low_bits == 4 else (-128, 127),
+                    out_low=out_buf(n * po * qo * 64, low_bits) if low_bits else None)
+        keys = [k for k in ("y", "out_low") if args[k] is not None]
+        cs, gs = run_both("maxpool_requant", args, keys)
+        for a, b in zip(cs, gs):
+            assert torch.equal(a, b), (shape, y_bits, low_bits)
+
+
+def test_avgpool_quantize_requant_dequant_pack():
+    r = rng(21)
+    n, c = 3, 512
+    for x_bits in (16, 32):
+        x = rand_act(r, n * 49 * c, x_bits)
+        if x_bits == 32:
+            x[:49 * c] = torch.from_numpy(r.randint(-3, 1, size=49 * c).astype(np.int32))   # negative sums
+        (a,), (b,) = run_both("avgpool_requant", dict(x=x, n=n, hw=49, c=c, x_bits=x_bits, me=dyadic(0.004 if x_bits == 16 else 0.9),
+                                                      clamp=(-128, 127), out=torch.zeros(n * c, dtype=torch.int8)), ["out"])
+        assert torch.equal(a, b)
+    xf = torch.from_numpy(r.randn(2, 3, 17, 13).astype(np.float32) * 2)
+    xf[0, 0, 0, :4] = torch.tensor([0.5, 1.5, 2.5, -0.5]) * 0.0173      # ties
+    (a,), (b,) = run_both("quantize_input", dict(x=xf, scale=0.0173, clamp=(-128, 127), out=torch.zeros(2 * 17 * 13 * 3, dtype=torch.int8)), ["out"])
+    assert torch.equal(a, b)
+    rows, ch = 37, 64
+    for x_bits, per_ch, out_bits in [(32, 1, 8), (16, 0, 4), (32, 1, 16), (16, 0, 8)]:
+        x = rand_act(r, rows * ch, x_bits)
+        chan = make_chan(r, ch if per_ch else 1, bias_mag=1 if not per_ch else 1000, ratio_lo=1e-3, ratio_hi=0.1)
+        clamp = {4: (0, 15), 8: (-128, 127), 16: (-32768, 32767)}[out_bits]
+        (a,), (b,) = run_both("requant", dict(x=x, rows=rows, c=ch, x_bits=x_bits, chan=chan, chan_stride=per_ch, relu=1, out_bits=out_bits,
+                                              clamp=clamp, out=out_buf(rows * ch, out_bits)), ["out"])
+        assert torch.equal(a, b)
+    acc = rand_act(r, rows * ch, 32)
+    chan = make_chan(r, ch, ratio_lo=0.01, ratio_hi=0.9)
+    for res_kind, res_bits, y_bits, low_bits in [(0, 16, 16, 8), (1, 32, 32, 4), (0, 32, 32, 0)]:
+        res = rand_act(r, rows * ch, res_bits if res_kind == 0 else 32)
+        ep = ops.epilogue(EPI_RESIDUAL, relu=1, res_kind=res_kind, res_bits=res_bits, res_me=dyadic(0.6), y_bits=y_bits, low_bits=low_bits,
+                          low_me=dyadic(0.002), low_clamp=(0, 15) if low_bits == 4 else (-128, 127))
+        args = dict(acc=acc, rows=rows, c=ch, chan=chan, ep=ep, res=res, res_chan=make_chan(r, ch, ratio_lo=0.01, ratio_hi=0.9) if res_kind else None,
+                    y=out_buf(rows * ch, y_bits), out_low=out_buf(rows * ch, low_bits) if low_bits else None)
+        keys = [k for k in ("y", "out_low") if args[k] is not None]
+        cs, gs = run_both("add_requant", args, keys)
+        for a, b in zip(cs, gs):
+            assert torch.equal(a, b)
+    for bits, signed in [(4, False), (8, True), (16, False), (32, True)]:
+        x = rand_act(r, 2 * 5 * 3 * 16, bits)
+        (a,), (b,) = run_both("dequant", dict(x=x, n=2, hh=5, ww=3, c=16, x_bits=bits, x_signed=signed, scale=0.0371, out=torch.zeros(2, 16, 5, 3)), ["out"])
+        assert torch.equal(a, b)
+    v = torch.from_numpy(r.randint(0, 16, size=4096).astype(np.uint8))
+    packed = torch.zeros(2048, dtype=torch.uint8, device=DEV)
+    ops.pack_i4(v.to(DEV), packed)
+    back = torch.zeros(4096, dtype=torch.uint8, device=DEV)
+    ops.unpack_i4(packed, back)
+    torch.cuda.synchronize()
+    assert torch.equal(packed.cpu(), torch.from_numpy(am.pack_i4(v.numpy()))) and torch.equal(back.cpu(), v)
+
+
+def test_bad_arguments_are_reported():
+    x = torch.zeros(64 * 4, dtype=torch.int8, device=DEV)
+    w = torch.zeros((64, 1, 1, 48), dtype=torch.int8, device=DEV)
+    chan = ops.make_chan([0] * 64, [0] * 64, [1] * 64).to(DEV)
+    with pytest.raises(HawqError, match="multiples of 64"):
+        ops.conv2d(x, ops.conv_desc(1, 2, 2, 48, 64, 1, 1, 1, 0, 8), ops.epilogue(EPI_REQUANT, out_bits=8, clamp=(-128, 127)), w, chan, out=x)
+    with pytest.raises(HawqError, match="requires relu"):
+        ops.conv2d(x, ops.conv_desc(1, 2, 2, 64, 64, 1, 1, 1, 0, 8), ops.epilogue(EPI_RESIDUAL, relu=0, res_bits=32, res_me=(1 << 30, 31), y_bits=16),
+                   w, chan, res=x, out=x)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.conv2d(x.cpu(), ops.conv_desc(1, 2, 2, 64, 64, 1, 1, 1, 0, 8), ops.epilogue(EPI_RAW_I32), w, chan, out=x)
