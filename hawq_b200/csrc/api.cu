@@ -139,6 +139,11 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   p.res_kind = ep->res_kind; p.res_bits = ep->res_bits; p.res_m = ep->res_m; p.res_e = ep->res_e;
   p.y_bits = ep->y_bits; p.low_bits = ep->low_bits; p.low_m = ep->low_m; p.low_e = ep->low_e;
   p.low_lo = ep->low_lo; p.low_hi = ep->low_hi; p.cout_store = ep->cout_store;
+  p.slow_scalar = 0;
+  if (ep->mode == HAWQ_EPI_RESIDUAL) {
+    if (ep->res_kind == 0 && !dyadic_is_fast(ep->res_m, ep->res_e)) p.slow_scalar = 1;
+    if (ep->low_bits != 0 && !dyadic_is_fast(ep->low_m, ep->low_e)) p.slow_scalar = 1;
+  }
 
   switch (ep->mode) {
     case HAWQ_EPI_REQUANT:

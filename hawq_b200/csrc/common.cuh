@@ -26,10 +26,28 @@ __host__ __device__ __forceinline__ int32_t rhe_requant(int32_t v, uint32_t m, i
 __device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) { return max(lo, min(v, hi)); }
 
 __device__ __forceinline__ int32_t sat_add(int32_t a, int32_t b) {
-  long long s = (long long)a + (long long)b;
-  s = s > 2147483647ll ? 2147483647ll : s;
-  s = s < -2147483648ll ? -2147483648ll : s;
-  return (int32_t)s;
+  int32_t r;
+  asm("add.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast exact path for the common case ratio = m * 2^-e <= 1 (every HAWQ ResNet layer):
+//   q = RHE(v * M),  M = m * 2^-e held as a double (exact: m <= 2^31, power-of-two scaling).
+// double(v) is built without a conversion instruction: bits(2^52 + 2^31 + v) = {0x43300000, v ^ 0x80000000}, minus
+// (2^52 + 2^31) is exact.  fma(double(v), M, 1.5 * 2^52) forms the exact product and rounds ONCE, to an integer
+// (ulp = 1 in [2^52, 2^53)), ties-to-even; the low mantissa word is q in two's complement (|q| <= |v| < 2^31).
+// = the reference's round(f64(v) * f64(m) / 2^e) whenever that product is exact in fp64, and the exact integer
+// result otherwise.  2 FP64 instructions + 1 LOP per value.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dyadic_to_double(uint32_t m, int32_t e) {
+  return (double)m * __hiloint2double((1023 - e) << 20, 0);   // m * 2^-e, exact
+}
+__host__ __device__ __forceinline__ bool dyadic_is_fast(uint32_t m, int32_t e) { return m == 0u || e >= 31; }
+
+__device__ __forceinline__ int32_t rhe_requant_fast(int32_t v, double M) {
+  const double dv = __hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)) - 4503601774854144.0;
+  return __double2loint(__fma_rn(dv, M, 6755399441055744.0));
 }
 
 // QuantAveragePool2d integer rule (quant_modules.py:585-602, quant_utils.py:324-341): trunc(sum/kk + 0.01).

@@ -12,6 +12,8 @@
 //   Epilogues (hawq_epilogue_mode): REQUANT (case 0 of fixedpoint_fn), RESIDUAL (case 1: dual dyadic requant + add,
 //   optional ReLU, writes the new residual stream and/or the next unit's low-bit activation), RAW_I32, DEQUANT_F32.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace hawq {
@@ -37,6 +39,7 @@ struct ConvParams {
   uint32_t low_m;
   int low_e, low_lo, low_hi;
   int cout_store;
+  int slow_scalar;   // host-checked: a scalar dyadic pair (res / low) has ratio > 1 -> generic 64-bit requant
 };
 
 constexpr int CONV_BM = 128;
@@ -52,7 +55,11 @@ struct ConvSmem {
   static constexpr int OUT_PITCH = BN + 16;
   static constexpr int OUT_STAGE = CONV_BM * OUT_PITCH;
   static constexpr int MAIN = PIPE > OUT_STAGE ? PIPE : OUT_STAGE;
-  static constexpr int TOTAL = MAIN + BN * (int)sizeof(hawq_chan);
+  static constexpr int CHAN_OFF = MAIN;                                    // hawq_chan[BN]
+  static constexpr int M_OFF = CHAN_OFF + BN * (int)sizeof(hawq_chan);     // double[BN]: m * 2^-e of chan
+  static constexpr int M1_OFF = M_OFF + BN * 8;                           // double[BN]: m * 2^-e of res_chan
+  static constexpr int RC_OFF = M1_OFF + BN * 8;                          // hawq_chan[BN]: res_chan
+  static constexpr int TOTAL = RC_OFF + BN * (int)sizeof(hawq_chan);
 };
 
 // swizzled byte offset of 16-byte chunk `ch` of row `row` (rows of 64 B: 4 chunks; rows of 32 B: 2 chunks)
@@ -77,7 +84,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) conv_igemm_kernel(const ConvP
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * S::A_STAGE;
-  hawq_chan* sChan = reinterpret_cast<hawq_chan*>(smem + S::MAIN);
+  hawq_chan* sChan = reinterpret_cast<hawq_chan*>(smem + S::CHAN_OFF);
+  double* sM = reinterpret_cast<double*>(smem + S::M_OFF);
+  double* sM1 = reinterpret_cast<double*>(smem + S::M1_OFF);
+  hawq_chan* sResChan = reinterpret_cast<hawq_chan*>(smem + S::RC_OFF);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -86,7 +96,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) conv_igemm_kernel(const ConvP
   const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
 
-  if (tid < BN) sChan[tid] = p.chan[n0 + tid];
+  int slow = p.slow_scalar;
+  if (tid < BN) {
+    const hawq_chan c = p.chan[n0 + tid];
+    sChan[tid] = c;
+    sM[tid] = dyadic_to_double(c.m, c.e);
+    slow |= !dyadic_is_fast(c.m, c.e);
+    if (p.mode == HAWQ_EPI_RESIDUAL && p.res_kind == 1) {
+      const hawq_chan rc = p.res_chan[n0 + tid];
+      sResChan[tid] = rc;
+      sM1[tid] = dyadic_to_double(rc.m, rc.e);
+      slow |= !dyadic_is_fast(rc.m, rc.e);
+    }
+  }
+  const bool use_slow = __syncthreads_or(slow) != 0;   // CTA-uniform: any ratio > 1 -> generic exact integer requant
 
   // ---- per-thread gather coordinates for the A rows this thread copies ----
   const int a_ch = tid % A_CH;
@@ -195,84 +218,100 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) conv_igemm_kernel(const ConvP
   const bool stage_low = (p.mode == HAWQ_EPI_REQUANT && p.out_bits <= 8) || (p.mode == HAWQ_EPI_RESIDUAL && p.low_bits != 0);
   const int stage_bits = (p.mode == HAWQ_EPI_REQUANT) ? p.out_bits : p.low_bits;
 
+  auto epilogue = [&](auto fast_tag) {
+    constexpr bool FAST = decltype(fast_tag)::value;
+    const double res_M = dyadic_to_double(p.res_m, p.res_e), low_M = dyadic_to_double(p.low_m, p.low_e);
+    auto rq = [&](int32_t v, uint32_t m, int e, double M) -> int32_t {
+      if constexpr (FAST) return rhe_requant_fast(v, M);
+      else return rhe_requant(v, m, e);
+    };
 #pragma unroll
-  for (int mi = 0; mi < 2; ++mi) {
+    for (int mi = 0; mi < 2; ++mi) {
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int row = wm * 32 + mi * 16 + hf * 8 + g;
-      const int m = m0 + row;
-      const bool ok = m < p.M;
+      for (int hf = 0; hf < 2; ++hf) {
+        const int row = wm * 32 + mi * 16 + hf * 8 + g;
+        const int m = m0 + row;
+        const bool ok = m < p.M;
 #pragma unroll
-      for (int ni = 0; ni < NT; ++ni) {
-        const int col = wn * WNT + ni * 8 + 2 * t;
-        const int4 c0 = *reinterpret_cast<const int4*>(&sChan[col]);
-        const int4 c1 = *reinterpret_cast<const int4*>(&sChan[col + 1]);
-        int32_t v0 = sat_add(acc[mi][ni][hf * 2 + 0], c0.x);
-        int32_t v1 = sat_add(acc[mi][ni][hf * 2 + 1], c1.x);
-        const size_t gidx = (size_t)m * p.Cout + n0 + col;
-        if (p.mode == HAWQ_EPI_REQUANT) {
-          if (p.relu) { v0 = max(v0, 0); v1 = max(v1, 0); }
-          const int32_t q0 = clampi(rhe_requant(v0, (uint32_t)c0.y, c0.z), p.lo, p.hi);
-          const int32_t q1 = clampi(rhe_requant(v1, (uint32_t)c1.y, c1.z), p.lo, p.hi);
-          if (p.out_bits <= 8) {
-            *reinterpret_cast<uint16_t*>(sOut + row * S::OUT_PITCH + col) = (uint16_t)((q0 & 0xFF) | ((q1 & 0xFF) << 8));
-          } else if (ok) {
-            if (p.out_bits == 16) {
-              *reinterpret_cast<uint32_t*>(reinterpret_cast<int16_t*>(p.out) + gidx) =
-                  (uint32_t)(q0 & 0xFFFF) | ((uint32_t)(q1 & 0xFFFF) << 16);
-            } else {
-              *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + gidx) = make_int2(q0, q1);
+        for (int ni = 0; ni < NT; ++ni) {
+          const int col = wn * WNT + ni * 8 + 2 * t;
+          const int4 c0 = *reinterpret_cast<const int4*>(&sChan[col]);
+          const int4 c1 = *reinterpret_cast<const int4*>(&sChan[col + 1]);
+          const double2 M01 = *reinterpret_cast<const double2*>(&sM[col]);
+          int32_t v0 = sat_add(acc[mi][ni][hf * 2 + 0], c0.x);
+          int32_t v1 = sat_add(acc[mi][ni][hf * 2 + 1], c1.x);
+          const size_t gidx = (size_t)m * p.Cout + n0 + col;
+          if (p.mode == HAWQ_EPI_REQUANT) {
+            if (p.relu) { v0 = max(v0, 0); v1 = max(v1, 0); }
+            const int32_t q0 = clampi(rq(v0, (uint32_t)c0.y, c0.z, M01.x), p.lo, p.hi);
+            const int32_t q1 = clampi(rq(v1, (uint32_t)c1.y, c1.z, M01.y), p.lo, p.hi);
+            if (p.out_bits <= 8) {
+              *reinterpret_cast<uint16_t*>(sOut + row * S::OUT_PITCH + col) = (uint16_t)((q0 & 0xFF) | ((q1 & 0xFF) << 8));
+            } else if (ok) {
+              if (p.out_bits == 16) {
+                *reinterpret_cast<uint32_t*>(reinterpret_cast<int16_t*>(p.out) + gidx) =
+                    (uint32_t)(q0 & 0xFFFF) | ((uint32_t)(q1 & 0xFFFF) << 16);
+              } else {
+                *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + gidx) = make_int2(q0, q1);
+              }
             }
-          }
-        } else if (p.mode == HAWQ_EPI_RESIDUAL) {
-          int32_t r0 = 0, r1 = 0;
-          uint32_t rm0 = p.res_m, rm1 = p.res_m;
-          int re0 = p.res_e, re1 = p.res_e;
-          if (ok) {
-            if (p.res_kind == 0 && p.res_bits == 16) {
-              const uint32_t pr = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.res) + gidx);
-              r0 = (int32_t)(pr & 0xFFFFu);
-              r1 = (int32_t)(pr >> 16);
-            } else {
-              const int2 pr = *reinterpret_cast<const int2*>(reinterpret_cast<const int32_t*>(p.res) + gidx);
-              r0 = pr.x;
-              r1 = pr.y;
-            }
-          }
-          if (p.res_kind == 1) {
-            const hawq_chan rc0 = p.res_chan[n0 + col], rc1 = p.res_chan[n0 + col + 1];
-            rm0 = rc0.m; re0 = rc0.e; rm1 = rc1.m; re1 = rc1.e;
-          }
-          int32_t y0 = sat_add(rhe_requant(r0, rm0, re0), rhe_requant(v0, (uint32_t)c0.y, c0.z));
-          int32_t y1 = sat_add(rhe_requant(r1, rm1, re1), rhe_requant(v1, (uint32_t)c1.y, c1.z));
-          if (p.relu) { y0 = max(y0, 0); y1 = max(y1, 0); }
-          if (p.y_bits == 32) {
-            if (ok) *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + gidx) = make_int2(y0, y1);
-          } else if (p.y_bits == 16) {
+          } else if (p.mode == HAWQ_EPI_RESIDUAL) {
+            int32_t r0 = 0, r1 = 0;
+            uint32_t rm0 = p.res_m, rm1 = p.res_m;
+            int re0 = p.res_e, re1 = p.res_e;
+            double rM0 = res_M, rM1 = res_M;
             if (ok) {
-              if (y0 > 65535 || y1 > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
-              *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out) + gidx) =
-                  (uint32_t)min(y0, 65535) | ((uint32_t)min(y1, 65535) << 16);
+              if (p.res_kind == 0 && p.res_bits == 16) {
+                const uint32_t pr = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.res) + gidx);
+                r0 = (int32_t)(pr & 0xFFFFu);
+                r1 = (int32_t)(pr >> 16);
+              } else {
+                const int2 pr = *reinterpret_cast<const int2*>(reinterpret_cast<const int32_t*>(p.res) + gidx);
+                r0 = pr.x;
+                r1 = pr.y;
+              }
             }
-          }
-          if (p.low_bits != 0) {
-            const int32_t q0 = clampi(rhe_requant(y0, p.low_m, p.low_e), p.low_lo, p.low_hi);
-            const int32_t q1 = clampi(rhe_requant(y1, p.low_m, p.low_e), p.low_lo, p.low_hi);
-            *reinterpret_cast<uint16_t*>(sOut + row * S::OUT_PITCH + col) = (uint16_t)((q0 & 0xFF) | ((q1 & 0xFF) << 8));
-          }
-        } else if (p.mode == HAWQ_EPI_RAW_I32) {
-          if (ok) *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + gidx) = make_int2(v0, v1);
-        } else {  // HAWQ_EPI_DEQUANT_F32
-          if (ok) {
-            float* o = reinterpret_cast<float*>(p.out) + (size_t)m * p.cout_store;
-            const int c = n0 + col;
-            if (c < p.cout_store) o[c] = __fmul_rn((float)v0, p.fscale[c]);
-            if (c + 1 < p.cout_store) o[c + 1] = __fmul_rn((float)v1, p.fscale[c + 1]);
+            if (p.res_kind == 1) {
+              if constexpr (FAST) {
+                const double2 M1 = *reinterpret_cast<const double2*>(&sM1[col]);
+                rM0 = M1.x; rM1 = M1.y;
+              } else {
+                rm0 = sResChan[col].m; re0 = sResChan[col].e; rm1 = sResChan[col + 1].m; re1 = sResChan[col + 1].e;
+              }
+            }
+            int32_t y0 = sat_add(rq(r0, rm0, re0, rM0), rq(v0, (uint32_t)c0.y, c0.z, M01.x));
+            int32_t y1 = sat_add(rq(r1, rm1, re1, rM1), rq(v1, (uint32_t)c1.y, c1.z, M01.y));
+            if (p.relu) { y0 = max(y0, 0); y1 = max(y1, 0); }
+            if (p.y_bits == 32) {
+              if (ok) *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + gidx) = make_int2(y0, y1);
+            } else if (p.y_bits == 16) {
+              if (ok) {
+                if (max(y0, y1) > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
+                *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out) + gidx) =
+                    (uint32_t)min(y0, 65535) | ((uint32_t)min(y1, 65535) << 16);
+              }
+            }
+            if (p.low_bits != 0) {
+              const int32_t q0 = clampi(rq(y0, p.low_m, p.low_e, low_M), p.low_lo, p.low_hi);
+              const int32_t q1 = clampi(rq(y1, p.low_m, p.low_e, low_M), p.low_lo, p.low_hi);
+              *reinterpret_cast<uint16_t*>(sOut + row * S::OUT_PITCH + col) = (uint16_t)((q0 & 0xFF) | ((q1 & 0xFF) << 8));
+            }
+          } else if (p.mode == HAWQ_EPI_RAW_I32) {
+            if (ok) *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + gidx) = make_int2(v0, v1);
+          } else {  // HAWQ_EPI_DEQUANT_F32
+            if (ok) {
+              float* o = reinterpret_cast<float*>(p.out) + (size_t)m * p.cout_store;
+              const int c = n0 + col;
+              if (c < p.cout_store) o[c] = __fmul_rn((float)v0, p.fscale[c]);
+              if (c + 1 < p.cout_store) o[c + 1] = __fmul_rn((float)v1, p.fscale[c + 1]);
+            }
           }
         }
       }
     }
-  }
+  };
+  if (use_slow) epilogue(std::false_type{});
+  else epilogue(std::true_type{});
 
   if (stage_low) {
     __syncthreads();

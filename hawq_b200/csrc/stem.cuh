@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const int8_t* __restrict
   __shared__ uint32_t sPatch[STEM_PH * STEM_PW];
   __shared__ uint32_t sW[64 * STEM_WPITCH];
   __shared__ hawq_chan sChan[64];
+  __shared__ double sM[64];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -31,7 +32,13 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const int8_t* __restrict
   const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
 
   for (int i = tid; i < 64 * 56; i += 256) sW[(i / 56) * STEM_WPITCH + (i % 56)] = w[i];
-  if (tid < 64) sChan[tid] = chan[tid];
+  int slow = 0;
+  if (tid < 64) {
+    const hawq_chan c = chan[tid];
+    sChan[tid] = c;
+    sM[tid] = dyadic_to_double(c.m, c.e);
+    slow = !dyadic_is_fast(c.m, c.e);
+  }
   for (int i = tid; i < STEM_PH * STEM_PW; i += 256) {
     const int py = i / STEM_PW, px = i - py * STEM_PW;
     const int iy = iy0 + py, ix = ix0 + px;
@@ -42,7 +49,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const int8_t* __restrict
     }
     sPatch[i] = v;
   }
-  __syncthreads();
+  const bool use_slow = __syncthreads_or(slow) != 0;
 
   int32_t acc[8][4];
 #pragma unroll
@@ -80,8 +87,17 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const int8_t* __restrict
     for (int j = 0; j < 8; ++j) {
       const int c = 8 * j + 2 * t;
       const hawq_chan c0 = sChan[c], c1 = sChan[c + 1];
-      int32_t q0 = clampi(rhe_requant(sat_add(acc[j][hf * 2 + 0], c0.bias), c0.m, c0.e), lo, hi);
-      int32_t q1 = clampi(rhe_requant(sat_add(acc[j][hf * 2 + 1], c1.bias), c1.m, c1.e), lo, hi);
+      const int32_t v0 = sat_add(acc[j][hf * 2 + 0], c0.bias), v1 = sat_add(acc[j][hf * 2 + 1], c1.bias);
+      int32_t q0, q1;
+      if (use_slow) {
+        q0 = rhe_requant(v0, c0.m, c0.e);
+        q1 = rhe_requant(v1, c1.m, c1.e);
+      } else {
+        q0 = rhe_requant_fast(v0, sM[c]);
+        q1 = rhe_requant_fast(v1, sM[c + 1]);
+      }
+      q0 = clampi(q0, lo, hi);
+      q1 = clampi(q1, lo, hi);
       q0 = max(q0, 0);
       q1 = max(q1, 0);
       *reinterpret_cast<uint32_t*>(o + c) = (uint32_t)(q0 & 0xFFFF) | ((uint32_t)(q1 & 0xFFFF) << 16);
@@ -133,10 +149,14 @@ __global__ void __launch_bounds__(256) maxpool_requant_kernel(const int16_t* __r
     }
     if (low_bits != 0) {
       uint32_t wlo = 0, whi = 0;
+      const bool fast = dyadic_is_fast(low_m, low_e);
+      const double low_M = dyadic_to_double(low_m, low_e);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        wlo |= (uint32_t)(clampi(rhe_requant(v[k], low_m, low_e), low_lo, low_hi) & 0xFF) << (8 * k);
-        whi |= (uint32_t)(clampi(rhe_requant(v[k + 4], low_m, low_e), low_lo, low_hi) & 0xFF) << (8 * k);
+        const int32_t qa = fast ? rhe_requant_fast(v[k], low_M) : rhe_requant(v[k], low_m, low_e);
+        const int32_t qb = fast ? rhe_requant_fast(v[k + 4], low_M) : rhe_requant(v[k + 4], low_m, low_e);
+        wlo |= (uint32_t)(clampi(qa, low_lo, low_hi) & 0xFF) << (8 * k);
+        whi |= (uint32_t)(clampi(qb, low_lo, low_hi) & 0xFF) << (8 * k);
       }
       if (low_bits == 8) {
         *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(out_low) + oidx) = make_uint2(wlo, whi);

@@ -76,6 +76,39 @@ def test_conv_requant(geom, a_bits):
         assert torch.equal(c_out, g_out), (geom, a_bits, out_bits)
 
 
+@pytest.mark.parametrize("ratio_kind", ["pow2_ties", "above_one_mixed"])
+def test_conv_requant_ties_and_generic_path(ratio_kind):
+    """Identity 1x1 weights make acc = x, so v = x + bias sweeps chosen integers: power-of-two ratios give exact .5 ties
+    (round-half-to-even, NOT TVM's half-up); ratios > 1 force the generic 64-bit requant instead of the FP64-FMA fast path."""
+    r = rng(99)
+    n, h, w, c = 2, 16, 16, 64
+    x = rand_act(r, n * h * w * c, 8)
+    wt = torch.zeros((c, 1, 1, c), dtype=torch.int8)
+    for i in range(c):
+        wt[i, 0, 0, i] = 1
+    if ratio_kind == "pow2_ties":
+        ratios = [2.0 ** -(i % 8 + 1) for i in range(c)]
+        bias = [1000 * i + 8 * (i % 3) for i in range(c)]
+    else:
+        ratios = [float(np.exp(r.uniform(np.log(0.3), np.log(6.0)))) for _ in range(c)]
+        bias = r.randint(-50000, 50000, size=c).tolist()
+    me = [dyadic(v) for v in ratios]
+    chan = ops.make_chan(bias, [m for m, _ in me], [e for _, e in me])
+    d = ops.conv_desc(n, h, w, c, c, 1, 1, 1, 0, 8)
+    for out_bits, clamp, relu in [(32, (-2 ** 31, 2 ** 31 - 1), 0), (16, (-32768, 32767), 0), (8, (-128, 127), 1)]:
+        ep = ops.epilogue(EPI_REQUANT, relu=relu, out_bits=out_bits, clamp=clamp)
+        (c_out,), (g_out,) = run_both("conv2d", dict(x=x, desc=d, ep=ep, w=wt, chan=chan, out=out_buf(n * h * w * c, out_bits)), ["out"])
+        assert torch.equal(c_out, g_out), (ratio_kind, out_bits)
+    # residual form with a scalar ratio > 1 on the identity operand and on the low-bit copy
+    res = rand_act(r, n * h * w * c, 32)
+    ep = ops.epilogue(EPI_RESIDUAL, relu=1, res_kind=0, res_bits=32, res_me=dyadic(1.5 if ratio_kind != "pow2_ties" else 0.25), y_bits=32,
+                      low_bits=8, low_me=dyadic(2.0 ** -7), low_clamp=(-128, 127))
+    cs, gs = run_both("conv2d", dict(x=x, desc=d, ep=ep, w=wt, chan=chan, res=res, out=out_buf(n * h * w * c, 32),
+                                     out_low=out_buf(n * h * w * c, 8)), ["out", "out_low"])
+    for a, b in zip(cs, gs):
+        assert torch.equal(a, b), ratio_kind
+
+
 @pytest.mark.parametrize("a_bits", [8, 4])
 @pytest.mark.parametrize("geom", CONV_GEOMS[:4])
 def test_conv_residual(geom, a_bits):
