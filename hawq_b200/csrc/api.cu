@@ -47,11 +47,27 @@ static int grid_for(long long work_items, int sm_count) {
   return (int)blocks;
 }
 
-template <int BN, bool A4>
-static int set_conv_attr() {
-  CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN, A4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int BN, bool A4, int EPI>
+static int set_conv_attr1() {
+  CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN, A4, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ConvSmem<BN, A4>::TOTAL));
   return HAWQ_OK;
+}
+template <int BN, bool A4>
+static int set_conv_attr() {
+  int rc;
+  if ((rc = set_conv_attr1<BN, A4, EPI_GENERIC>()) || (rc = set_conv_attr1<BN, A4, EPI_FAST_LOW>()) ||
+      (rc = set_conv_attr1<BN, A4, EPI_FAST_RES>()))
+    return rc;
+  return HAWQ_OK;
+}
+
+template <int BN, bool A4>
+static void launch_conv(const ConvParams& p, dim3 grid, cudaStream_t s) {
+  const int smem = ConvSmem<BN, A4>::TOTAL;
+  if (p.mode == HAWQ_EPI_REQUANT && p.out_bits <= 8) conv_igemm_kernel<BN, A4, EPI_FAST_LOW><<<grid, CONV_THREADS, smem, s>>>(p);
+  else if (p.mode == HAWQ_EPI_RESIDUAL) conv_igemm_kernel<BN, A4, EPI_FAST_RES><<<grid, CONV_THREADS, smem, s>>>(p);
+  else conv_igemm_kernel<BN, A4, EPI_GENERIC><<<grid, CONV_THREADS, smem, s>>>(p);
 }
 
 extern "C" {
@@ -187,11 +203,11 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   const dim3 grid((unsigned)((M + CONV_BM - 1) / CONV_BM), (unsigned)(d->Cout / (bn128 ? 128 : 64)), 1);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->a_bits == 8) {
-    if (bn128) conv_igemm_kernel<128, false><<<grid, CONV_THREADS, ConvSmem<128, false>::TOTAL, s>>>(p);
-    else conv_igemm_kernel<64, false><<<grid, CONV_THREADS, ConvSmem<64, false>::TOTAL, s>>>(p);
+    if (bn128) launch_conv<128, false>(p, grid, s);
+    else launch_conv<64, false>(p, grid, s);
   } else {
-    if (bn128) conv_igemm_kernel<128, true><<<grid, CONV_THREADS, ConvSmem<128, true>::TOTAL, s>>>(p);
-    else conv_igemm_kernel<64, true><<<grid, CONV_THREADS, ConvSmem<64, true>::TOTAL, s>>>(p);
+    if (bn128) launch_conv<128, true>(p, grid, s);
+    else launch_conv<64, true>(p, grid, s);
   }
   return launch_check("conv_igemm");
 }

@@ -54,12 +54,15 @@ struct ConvSmem {
   static constexpr int PIPE = CONV_STAGES * (A_STAGE + B_STAGE);
   static constexpr int OUT_PITCH = BN + 16;
   static constexpr int OUT_STAGE = CONV_BM * OUT_PITCH;
-  static constexpr int MAIN = PIPE > OUT_STAGE ? PIPE : OUT_STAGE;
-  static constexpr int CHAN_OFF = MAIN;                                    // hawq_chan[BN]
+  static constexpr int RES_TILE = CONV_BM * (BN * 4 + 32);                 // residual tile, worst case int32 + padding
+  static constexpr int MAIN = PIPE > RES_TILE ? PIPE : RES_TILE;          // pipeline ring, later the residual / y tile
+  static constexpr int OUT_OFF = MAIN;                                     // low-bit output staging tile
+  static constexpr int CHAN_OFF = OUT_OFF + OUT_STAGE;                     // hawq_chan[BN]
   static constexpr int M_OFF = CHAN_OFF + BN * (int)sizeof(hawq_chan);     // double[BN]: m * 2^-e of chan
   static constexpr int M1_OFF = M_OFF + BN * 8;                           // double[BN]: m * 2^-e of res_chan
   static constexpr int RC_OFF = M1_OFF + BN * 8;                          // hawq_chan[BN]: res_chan
-  static constexpr int TOTAL = RC_OFF + BN * (int)sizeof(hawq_chan);
+  static constexpr int CB_OFF = RC_OFF + BN * (int)sizeof(hawq_chan);     // double[BN]: 2^52 + 2^31 - bias
+  static constexpr int TOTAL = CB_OFF + BN * 8;
 };
 
 // swizzled byte offset of 16-byte chunk `ch` of row `row` (rows of 64 B: 4 chunks; rows of 32 B: 2 chunks)
@@ -69,7 +72,11 @@ __device__ __forceinline__ int swz(int row, int ch) {
   else return row * 32 + ((ch ^ ((row >> 2) & 1)) << 4);
 }
 
-template <int BN, bool A4>
+// EPI selects the compile-time specialised fast epilogue (used when every dyadic ratio of the launch is <= 1, which the
+// kernel verifies): 0 = none (generic run-time epilogue only), 1 = REQUANT to 4/8 bits, 2 = RESIDUAL.
+constexpr int EPI_GENERIC = 0, EPI_FAST_LOW = 1, EPI_FAST_RES = 2;
+
+template <int BN, bool A4, int EPI>
 __global__ void __launch_bounds__(CONV_THREADS, 2) conv_igemm_kernel(const ConvParams p) {
   using S = ConvSmem<BN, A4>;
   constexpr int BM = CONV_BM, STAGES = CONV_STAGES;
@@ -88,6 +95,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) conv_igemm_kernel(const ConvP
   double* sM = reinterpret_cast<double*>(smem + S::M_OFF);
   double* sM1 = reinterpret_cast<double*>(smem + S::M1_OFF);
   hawq_chan* sResChan = reinterpret_cast<hawq_chan*>(smem + S::RC_OFF);
+  double* sCb = reinterpret_cast<double*>(smem + S::CB_OFF);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -101,6 +109,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) conv_igemm_kernel(const ConvP
     const hawq_chan c = p.chan[n0 + tid];
     sChan[tid] = c;
     sM[tid] = dyadic_to_double(c.m, c.e);
+    sCb[tid] = 4503601774854144.0 - (double)c.bias;   // exact: folds the bias add into the int -> double conversion
     slow |= !dyadic_is_fast(c.m, c.e);
     if (p.mode == HAWQ_EPI_RESIDUAL && p.res_kind == 1) {
       const hawq_chan rc = p.res_chan[n0 + tid];
@@ -211,12 +220,123 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) conv_igemm_kernel(const ConvP
     }
   }
   cp_async_wait<0>();
-  __syncthreads();   // pipeline buffers are free: reused as the low-bit output staging tile
+  __syncthreads();   // pipeline buffers are free: reused for the residual tile (RESIDUAL epilogue)
+
+  // RESIDUAL: bulk-load this tile of the residual operand (coalesced 16 B cp.async, zero-fill past M) instead of
+  // issuing dependent scalar loads inside the epilogue; padded pitch keeps the fragment-pattern reads conflict-free.
+  uint8_t* sRes = smem;
+  const int res_es = (p.mode == HAWQ_EPI_RESIDUAL) ? ((p.res_kind == 1 || p.res_bits == 32) ? 4 : 2) : 0;
+  const int res_pitch = BN * res_es + 8 * res_es;
+  if (res_es) {
+    const int cpr = BN * res_es / 16;   // 16-byte chunks per row
+    const uint8_t* gres = reinterpret_cast<const uint8_t*>(p.res);
+    for (int id = tid; id < BM * cpr; id += CONV_THREADS) {
+      const int row = id / cpr, j = id - row * cpr;
+      const bool v = m0 + row < p.M;
+      const uint8_t* src = v ? gres + ((size_t)(m0 + row) * p.Cout + n0) * res_es + j * 16 : gres;
+      cp_async_16(smem_u32(sRes + row * res_pitch + j * 16), src, v ? 16 : 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+  const bool y_in_place = res_es != 0 && p.y_bits == res_es * 8;   // new residual stream overwrites the tile in smem
 
   // ------------------------------------------------------------------------------------------------ epilogue
-  uint8_t* sOut = smem;
+  uint8_t* sOut = smem + S::OUT_OFF;
   const bool stage_low = (p.mode == HAWQ_EPI_REQUANT && p.out_bits <= 8) || (p.mode == HAWQ_EPI_RESIDUAL && p.low_bits != 0);
   const int stage_bits = (p.mode == HAWQ_EPI_REQUANT) ? p.out_bits : p.low_bits;
+
+  constexpr double kMagic = 6755399441055744.0;      // 1.5 * 2^52
+  constexpr double kOffS = 4503601774854144.0;       // 2^52 + 2^31 (signed int -> double)
+  constexpr double kOffU = 4503599627370496.0;       // 2^52        (non-negative int -> double)
+  bool fast_done = false;
+
+  if constexpr (EPI == EPI_FAST_LOW) {
+    if (!use_slow) {
+      fast_done = true;
+      // clamp(RHE((acc + bias) * M)), ReLU folded into the lower clamp bound (RHE is monotone, RHE(0) = 0)
+      const int lo = p.relu ? max(p.lo, 0) : p.lo, hi = p.hi;
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) {
+        const int col = wn * WNT + ni * 8 + 2 * t;
+        const double2 Cb = *reinterpret_cast<const double2*>(&sCb[col]);
+        const double2 M = *reinterpret_cast<const double2*>(&sM[col]);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int row = wm * 32 + mi * 16 + hf * 8 + g;
+            const double d0 = __hiloint2double(0x43300000, acc[mi][ni][hf * 2 + 0] ^ 0x80000000) - Cb.x;
+            const double d1 = __hiloint2double(0x43300000, acc[mi][ni][hf * 2 + 1] ^ 0x80000000) - Cb.y;
+            const int q0 = clampi(__double2loint(__fma_rn(d0, M.x, kMagic)), lo, hi);
+            const int q1 = clampi(__double2loint(__fma_rn(d1, M.y, kMagic)), lo, hi);
+            *reinterpret_cast<uint16_t*>(sOut + row * S::OUT_PITCH + col) = (uint16_t)__byte_perm(q0, q1, 0x0040);
+          }
+        }
+      }
+    }
+  }
+
+  if constexpr (EPI == EPI_FAST_RES) {
+    if (!use_slow) {
+      fast_done = true;
+      const double res_M = dyadic_to_double(p.res_m, p.res_e), low_M = dyadic_to_double(p.low_m, p.low_e);
+      const int relu_floor = p.relu ? 0 : (int)0x80000000;
+      int ymax = 0;
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) {
+        const int col = wn * WNT + ni * 8 + 2 * t;
+        const double2 Cb = *reinterpret_cast<const double2*>(&sCb[col]);
+        const double2 M = *reinterpret_cast<const double2*>(&sM[col]);
+        double2 M1 = make_double2(res_M, res_M);
+        if (p.res_kind == 1) M1 = *reinterpret_cast<const double2*>(&sM1[col]);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int row = wm * 32 + mi * 16 + hf * 8 + g;
+            const double d0 = __hiloint2double(0x43300000, acc[mi][ni][hf * 2 + 0] ^ 0x80000000) - Cb.x;
+            const double d1 = __hiloint2double(0x43300000, acc[mi][ni][hf * 2 + 1] ^ 0x80000000) - Cb.y;
+            const int v0 = __double2loint(__fma_rn(d0, M.x, kMagic));
+            const int v1 = __double2loint(__fma_rn(d1, M.y, kMagic));
+            uint8_t* rptr = sRes + row * res_pitch + col * res_es;
+            double r0, r1;
+            if (res_es == 2) {   // uint16 residual stream: non-negative, no sign fix-up
+              const uint32_t pr = *reinterpret_cast<const uint32_t*>(rptr);
+              r0 = __hiloint2double(0x43300000, (int)(pr & 0xFFFFu)) - kOffU;
+              r1 = __hiloint2double(0x43300000, (int)(pr >> 16)) - kOffU;
+            } else {
+              const int2 pr = *reinterpret_cast<const int2*>(rptr);
+              r0 = __hiloint2double(0x43300000, pr.x ^ 0x80000000) - kOffS;
+              r1 = __hiloint2double(0x43300000, pr.y ^ 0x80000000) - kOffS;
+            }
+            int y0 = max(sat_add(__double2loint(__fma_rn(r0, M1.x, kMagic)), v0), relu_floor);
+            int y1 = max(sat_add(__double2loint(__fma_rn(r1, M1.y, kMagic)), v1), relu_floor);
+            if (p.y_bits == 16) {
+              ymax = max(ymax, max(y0, y1));
+              const uint32_t packed = (uint32_t)min(y0, 65535) | ((uint32_t)min(y1, 65535) << 16);
+              if (y_in_place) *reinterpret_cast<uint32_t*>(rptr) = packed;
+              else if (m0 + row < p.M)
+                *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out) + (size_t)(m0 + row) * p.Cout + n0 + col) = packed;
+            } else if (p.y_bits == 32) {
+              if (y_in_place) *reinterpret_cast<int2*>(rptr) = make_int2(y0, y1);
+              else if (m0 + row < p.M)
+                *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + (size_t)(m0 + row) * p.Cout + n0 + col) = make_int2(y0, y1);
+            }
+            if (p.low_bits != 0) {
+              const double l0 = __hiloint2double(0x43300000, y0 ^ 0x80000000) - kOffS;
+              const double l1 = __hiloint2double(0x43300000, y1 ^ 0x80000000) - kOffS;
+              const int q0 = clampi(__double2loint(__fma_rn(l0, low_M, kMagic)), p.low_lo, p.low_hi);
+              const int q1 = clampi(__double2loint(__fma_rn(l1, low_M, kMagic)), p.low_lo, p.low_hi);
+              *reinterpret_cast<uint16_t*>(sOut + row * S::OUT_PITCH + col) = (uint16_t)__byte_perm(q0, q1, 0x0040);
+            }
+          }
+        }
+      }
+      if (p.y_bits == 16 && ymax > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
+    }
+  }
 
   auto epilogue = [&](auto fast_tag) {
     constexpr bool FAST = decltype(fast_tag)::value;
@@ -260,16 +380,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) conv_igemm_kernel(const ConvP
             uint32_t rm0 = p.res_m, rm1 = p.res_m;
             int re0 = p.res_e, re1 = p.res_e;
             double rM0 = res_M, rM1 = res_M;
-            if (ok) {
-              if (p.res_kind == 0 && p.res_bits == 16) {
-                const uint32_t pr = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.res) + gidx);
-                r0 = (int32_t)(pr & 0xFFFFu);
-                r1 = (int32_t)(pr >> 16);
-              } else {
-                const int2 pr = *reinterpret_cast<const int2*>(reinterpret_cast<const int32_t*>(p.res) + gidx);
-                r0 = pr.x;
-                r1 = pr.y;
-              }
+            uint8_t* rptr = sRes + row * res_pitch + col * res_es;
+            if (res_es == 2) {
+              const uint32_t pr = *reinterpret_cast<const uint32_t*>(rptr);
+              r0 = (int32_t)(pr & 0xFFFFu);
+              r1 = (int32_t)(pr >> 16);
+            } else {
+              const int2 pr = *reinterpret_cast<const int2*>(rptr);
+              r0 = pr.x;
+              r1 = pr.y;
             }
             if (p.res_kind == 1) {
               if constexpr (FAST) {
@@ -283,13 +402,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) conv_igemm_kernel(const ConvP
             int32_t y1 = sat_add(rq(r1, rm1, re1, rM1), rq(v1, (uint32_t)c1.y, c1.z, M01.y));
             if (p.relu) { y0 = max(y0, 0); y1 = max(y1, 0); }
             if (p.y_bits == 32) {
-              if (ok) *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + gidx) = make_int2(y0, y1);
+              if (y_in_place) *reinterpret_cast<int2*>(rptr) = make_int2(y0, y1);
+              else if (ok) *reinterpret_cast<int2*>(reinterpret_cast<int32_t*>(p.out) + gidx) = make_int2(y0, y1);
             } else if (p.y_bits == 16) {
-              if (ok) {
-                if (max(y0, y1) > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
-                *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out) + gidx) =
-                    (uint32_t)min(y0, 65535) | ((uint32_t)min(y1, 65535) << 16);
-              }
+              if (ok && max(y0, y1) > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
+              const uint32_t packed = (uint32_t)min(y0, 65535) | ((uint32_t)min(y1, 65535) << 16);
+              if (y_in_place) *reinterpret_cast<uint32_t*>(rptr) = packed;
+              else if (ok) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out) + gidx) = packed;
             }
             if (p.low_bits != 0) {
               const int32_t q0 = clampi(rq(y0, p.low_m, p.low_e, low_M), p.low_lo, p.low_hi);
@@ -310,11 +429,23 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) conv_igemm_kernel(const ConvP
       }
     }
   };
-  if (use_slow) epilogue(std::false_type{});
-  else epilogue(std::true_type{});
+  if (!fast_done) {
+    if (use_slow) epilogue(std::false_type{});
+    else epilogue(std::true_type{});
+  }
 
+  if (y_in_place || stage_low) __syncthreads();
+  if (y_in_place) {   // coalesced copy-out of the new residual stream tile
+    const int cpr = BN * res_es / 16;
+    uint8_t* gy = reinterpret_cast<uint8_t*>(p.out);
+    for (int id = tid; id < BM * cpr; id += CONV_THREADS) {
+      const int row = id / cpr, j = id - row * cpr;
+      if (m0 + row < p.M)
+        *reinterpret_cast<int4*>(gy + ((size_t)(m0 + row) * p.Cout + n0) * res_es + j * 16) =
+            *reinterpret_cast<const int4*>(sRes + row * res_pitch + j * 16);
+    }
+  }
   if (stage_low) {
-    __syncthreads();
     uint8_t* gout = reinterpret_cast<uint8_t*>(p.mode == HAWQ_EPI_REQUANT ? p.out : p.out_low);
     if (stage_bits == 8) {
       constexpr int CPR = BN / 16;
