@@ -34,11 +34,14 @@ class hawq_epilogue_desc(C.Structure):
     _fields_ = [("mode", C.c_int32), ("relu", C.c_int32), ("out_bits", C.c_int32), ("clamp_lo", C.c_int32),
                 ("clamp_hi", C.c_int32), ("res_kind", C.c_int32), ("res_bits", C.c_int32), ("res_m", C.c_uint32),
                 ("res_e", C.c_int32), ("y_bits", C.c_int32), ("low_bits", C.c_int32), ("low_m", C.c_uint32),
-                ("low_e", C.c_int32), ("low_lo", C.c_int32), ("low_hi", C.c_int32), ("cout_store", C.c_int32)]
+                ("low_e", C.c_int32), ("low_lo", C.c_int32), ("low_hi", C.c_int32), ("cout_store", C.c_int32),
+                ("flags", C.c_int32)]
 
 
 EPI_REQUANT, EPI_RESIDUAL, EPI_RAW_I32, EPI_DEQUANT_F32 = 0, 1, 2, 3
 FLAG_RESIDUAL_OVERFLOW = 1
+FLAG_BAD_RATIO = 2
+EP_RATIOS_LE_ONE = 1
 
 _vp, _i32, _i64, _u32, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float
 _conv_args = [_vp, C.POINTER(hawq_conv_desc), C.POINTER(hawq_epilogue_desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]

@@ -5,7 +5,10 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "conv_igemm.cuh"
+#include "conv_tc.cuh"
 #include "elementwise.cuh"
 #include "stem.cuh"
 
@@ -88,6 +91,8 @@ int hawq_create(int device, hawq_handle** out) {
   CUDA_TRY(cudaMalloc(&h->status, sizeof(int32_t)));
   CUDA_TRY(cudaMemset(h->status, 0, sizeof(int32_t)));
   int rc;
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::TOTAL));
   if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
       (rc = set_conv_attr<64, true>()))
     return rc;
@@ -197,6 +202,19 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
       break;
     default:
       return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d: unknown epilogue mode %d", ep->mode);
+  }
+
+  // tcgen05 path: int8 activations, the three hot epilogues, all ratios <= 1 (promised), HAWQ_B200_TC != 0
+  static const bool tc_enabled = [] { const char* e = getenv("HAWQ_B200_TC"); return !(e && e[0] == '0'); }();
+  const bool tc_epi = (ep->mode == HAWQ_EPI_REQUANT && ep->out_bits <= 8) || ep->mode == HAWQ_EPI_RESIDUAL || ep->mode == HAWQ_EPI_RAW_I32;
+  if (tc_enabled && d->a_bits == 8 && tc_epi && (ep->flags & HAWQ_EP_RATIOS_LE_ONE) && !p.slow_scalar) {
+    const bool wide = (d->Cout % 128 == 0);
+    const long long tiles = ((M + TC_BM - 1) / TC_BM) * (d->Cout / (wide ? 128 : 64));
+    const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (wide) conv_tc_kernel<128><<<grid, TC_THREADS, TcSmem<128>::TOTAL, st>>>(p);
+    else conv_tc_kernel<64><<<grid, TC_THREADS, TcSmem<64>::TOTAL, st>>>(p);
+    return launch_check("conv_tc");
   }
 
   const bool bn128 = (d->Cout % 128 == 0);

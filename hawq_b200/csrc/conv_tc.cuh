@@ -1,0 +1,470 @@
+// Persistent warp-specialised implicit-GEMM convolution on 5th-gen tensor cores (tcgen05.mma kind::i8, TMEM
+// accumulators) with the HAWQ epilogues fused.  One CTA per SM loops over 128 x BN output tiles.
+//
+//   warps 0-3   producers: gather the A (im2col rows, zero-filled halo) and B (weights) k-tiles with 16-byte cp.async
+//               into a STAGES-deep shared-memory ring laid out in the UMMA canonical K-major SWIZZLE_64B format
+//               (rows of 64 int8, 16-byte chunk index XOR (row >> 1) & 3), then fence.proxy.async + mbarrier arrive;
+//   warp  4     allocates TMEM, one elected lane issues tcgen05.mma (M = 128, N = BN, K = 32; two per k-tile) into one
+//               of two TMEM accumulator buffers, tcgen05.commit releases smem stages / publishes the accumulator;
+//   warps 5-12  epilogue: tcgen05.ld the accumulator (thread = output row, 32 consecutive channels per load),
+//               exact FP64-FMA dyadic requantisation, residual add, ReLU, low-bit copy; every warp owns a private
+//               shared-memory slice (residual tile in, outputs staged in place) so only __syncwarp is needed, and all
+//               global traffic is full-line coalesced.
+//   While the epilogue of tile i runs, the producers and the MMA warp are already working on tile i+1.
+//
+// Supported: a_bits == 8 (signed), epilogue REQUANT -> 4/8 bit, RESIDUAL, RAW_I32, all dyadic ratios <= 1 (promised by
+// the caller through slow_scalar == 0 / HAWQ_EP_RATIOS_LE_ONE and re-checked here: a violation raises
+// HAWQ_FLAG_BAD_RATIO in the status word instead of producing wrong numbers).  Everything else uses conv_igemm.cuh.
+// Every mbarrier wait is bounded: a protocol bug traps (launch failure) instead of hanging the GPU.
+#pragma once
+#include "common.cuh"
+#include "conv_igemm.cuh"
+
+namespace hawq {
+
+constexpr int TC_BM = 128;
+constexpr int TC_STAGES = 6;
+constexpr int TC_LAG = 3;                 // producer signals k-tile (it - LAG) after issuing k-tile it
+constexpr int TC_PRODUCER_WARPS = 4;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_MMA_WARP = TC_PRODUCER_WARPS;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + TC_EPI_WARPS) * 32;   // 416
+
+template <int BN>
+struct TcSmem {
+  static constexpr int A_STAGE = TC_BM * 64;
+  static constexpr int B_STAGE = BN * 64;
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int RING = TC_STAGES * STAGE;
+  static constexpr int COLS_PER_WARP = BN / 2;
+  static constexpr int SLICE_PITCH = COLS_PER_WARP * 4 + 16;              // worst case int32 + 16 B pad (conflict-free)
+  static constexpr int SLICE = 32 * SLICE_PITCH;
+  static constexpr int LOW_PITCH = COLS_PER_WARP + 16;
+  static constexpr int LOW_SLICE = 32 * LOW_PITCH;
+  static constexpr int SLICES_OFF = RING;
+  static constexpr int LOW_OFF = SLICES_OFF + TC_EPI_WARPS * SLICE;
+  static constexpr int CST_OFF = LOW_OFF + TC_EPI_WARPS * LOW_SLICE;      // double2 {Cb, M}[BN]
+  static constexpr int M1_OFF = CST_OFF + BN * 16;                        // double M1[BN]
+  static constexpr int BAR_OFF = M1_OFF + BN * 8;                         // mbarriers + tmem base
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;                      // + slack for 1024 B alignment of the ring
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a broken pipeline protocol becomes a trap (cudaErrorLaunchFailure), never a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t i = 0; i < 20000000u; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], int8 x int8 -> int32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives row (lane quarter base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row atoms of 512 B (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
+// instruction descriptor: D = S32, A/B = signed int8, K-major both, N, M
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n, bool a_signed) {
+  return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams p) {
+  using S = TcSmem<BN>;
+  constexpr int BM = TC_BM, STAGES = TC_STAGES;
+  constexpr int CW = S::COLS_PER_WARP;           // columns handled by one epilogue warp: 32 or 64
+  constexpr int TMEM_COLS = 2 * BN;              // two accumulator buffers (power of two >= 32: 128 / 256)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_u32(smem);
+  double2* sCst = reinterpret_cast<double2*>(smem + S::CST_OFF);
+  double* sM1 = reinterpret_cast<double*>(smem + S::M1_OFF);
+  const uint32_t bar_base = smem_base + S::BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::BAR_OFF + 8 * (2 * STAGES + 4));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.Cout / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int KT = p.KH * p.KW * p.cin_chunks;
+
+  // ---- one-time setup ----
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), TC_PRODUCER_WARPS * 32);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), TC_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == TC_MMA_WARP) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < TC_PRODUCER_WARPS) {
+    // =============================================================================== producers (128 threads)
+    const int row = tid;                       // A row of the tile owned by this thread
+    uint32_t it = 0;                           // global k-tile counter (ring position)
+    uint32_t pending = 0;                      // k-tiles issued but not yet signalled
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int m = m0 + row;
+      const bool a_ok = m < p.M;
+      const int mm = a_ok ? m : 0;
+      const int n = mm / (p.Ho * p.Wo);
+      const int r = mm - n * (p.Ho * p.Wo);
+      const int ho = r / p.Wo, wo = r - ho * p.Wo;
+      const int hi0 = ho * p.stride - p.pad, wi0 = wo * p.stride - p.pad, pix = n * p.H * p.W;
+      int c = 0, kw = 0, kh = 0;
+      for (int kt = 0; kt < KT; ++kt, ++it) {
+        const int stage = it % STAGES;
+        mbar_wait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
+        const uint32_t a_base = smem_base + stage * S::STAGE;
+        const uint32_t b_base = a_base + S::A_STAGE;
+        {
+          const int hi = hi0 + kh, wi = wi0 + kw;
+          const bool v = a_ok && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W;
+          const uint8_t* src = v ? p.x + (size_t)(pix + hi * p.W + wi) * p.x_pix_bytes + c * 64 : p.x;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) cp_async_16(a_base + swz<64>(row, ch), src + ch * 16, v ? 16 : 0);
+        }
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {     // B: BN rows x 4 chunks over 128 threads
+          const int id = tid + i * 128;
+          const int brow = id >> 2, ch = id & 3;
+          cp_async_16(b_base + swz<64>(brow, ch), p.w + (size_t)(n0 + brow) * p.K + kt * 64 + ch * 16, 16);
+        }
+        cp_async_commit();
+        ++pending;
+        if (pending > TC_LAG) {                 // the group issued LAG iterations ago has landed
+          cp_async_wait<TC_LAG>();
+          fence_proxy_async();
+          mbar_arrive(full_bar((it - TC_LAG) % STAGES));
+          --pending;
+        }
+        if (++c == p.cin_chunks) { c = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
+      }
+    }
+    // drain
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (uint32_t j = pending; j > 0; --j) mbar_arrive(full_bar((it - j) % STAGES));
+  } else if (warp == TC_MMA_WARP) {
+    // =============================================================================== MMA issuer
+    const uint32_t idesc = umma_idesc_i8(BM, BN, true);
+    uint32_t it = 0, tile_iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+      const int buf = tile_iter & 1;
+      mbar_wait(tempty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kt = 0; kt < KT; ++kt, ++it) {
+        const int stage = it % STAGES;
+        mbar_wait(full_bar(stage), (it / STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_base + stage * S::STAGE;
+          const uint32_t b_addr = a_addr + S::A_STAGE;
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_i8(d_tmem, umma_desc_sw64(a_addr + k * 32), umma_desc_sw64(b_addr + k * 32), idesc, (kt | k) != 0);
+          umma_commit(empty_bar(stage));                          // smem stage reusable once these MMAs retire
+          if (kt == KT - 1) umma_commit(tfull_bar(buf));          // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================================================================== epilogue (8 warps)
+    const int ew = warp - (TC_MMA_WARP + 1);     // 0..7
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                    // column half
+    const int row = quarter * 32 + lane;         // tile row owned by this thread
+    uint8_t* slice = smem + S::SLICES_OFF + ew * S::SLICE;
+    uint8_t* lowslice = smem + S::LOW_OFF + ew * S::LOW_SLICE;
+    const bool is_res = p.mode == HAWQ_EPI_RESIDUAL;
+    const int res_es = is_res ? ((p.res_kind == 1 || p.res_bits == 32) ? 4 : 2) : 0;
+    const int y_es = is_res ? p.y_bits / 8 : (p.mode == HAWQ_EPI_RAW_I32 ? 4 : 0);   // bytes per element staged in `slice`
+    const int slice_pitch = CW * (res_es > y_es ? res_es : y_es) + 16;
+    const int low_bits = is_res ? p.low_bits : (p.mode == HAWQ_EPI_REQUANT ? p.out_bits : 0);
+    const double res_M = dyadic_to_double(p.res_m, p.res_e), low_M = dyadic_to_double(p.low_m, p.low_e);
+    const int relu_floor = p.relu ? 0 : (int)0x80000000;
+    const int q_lo = (p.mode == HAWQ_EPI_REQUANT) ? (p.relu ? max(p.lo, 0) : p.lo) : p.low_lo;
+    const int q_hi = (p.mode == HAWQ_EPI_REQUANT) ? p.hi : p.low_hi;
+    constexpr double kMagic = 6755399441055744.0, kOffS = 4503601774854144.0, kOffU = 4503599627370496.0;
+    int ymax = 0, bad = 0;
+    int cur_n0 = -1;
+    uint32_t tile_iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int buf = tile_iter & 1;
+      const int c0 = n0 + half * CW;             // first global channel of this warp
+
+      // per-channel constants of this tile's channel block (shared by the 8 epilogue warps; warp ew loads BN/8)
+      if (n0 != cur_n0) {
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32));     // everyone finished reading the previous block
+        for (int i = tid - (TC_MMA_WARP + 1) * 32; i < BN; i += TC_EPI_WARPS * 32) {
+          const hawq_chan ch = p.chan[n0 + i];
+          sCst[i] = make_double2(kOffS - (double)ch.bias, dyadic_to_double(ch.m, ch.e));
+          bad |= !dyadic_is_fast(ch.m, ch.e);
+          if (is_res && p.res_kind == 1) {
+            const hawq_chan rc = p.res_chan[n0 + i];
+            sM1[i] = dyadic_to_double(rc.m, rc.e);
+            bad |= !dyadic_is_fast(rc.m, rc.e);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32));
+        cur_n0 = n0;
+      }
+
+      // residual slice: 32 rows x CW columns, coalesced (a warp instruction covers whole rows)
+      if (res_es) {
+        const int cpr = CW * res_es / 16;
+        const uint8_t* gres = reinterpret_cast<const uint8_t*>(p.res);
+        for (int id = lane; id < 32 * cpr; id += 32) {
+          const int rr = id / cpr, j = id - rr * cpr;
+          const int gm = m0 + quarter * 32 + rr;
+          const bool v = gm < p.M;
+          const uint8_t* src = v ? gres + ((size_t)gm * p.Cout + c0) * res_es + j * 16 : gres;
+          cp_async_16(smem_u32(slice + rr * slice_pitch + j * 16), src, v ? 16 : 0);
+        }
+        cp_async_commit();
+      }
+
+      mbar_wait(tfull_bar(buf), (tile_iter >> 1) & 1);
+      tc_fence_after();
+      if (res_es) {
+        cp_async_wait<0>();
+        __syncwarp();
+      }
+      uint8_t* myrow = slice + lane * slice_pitch;
+      uint8_t* mylow = lowslice + lane * S::LOW_PITCH;
+
+#pragma unroll 1
+      for (int cb = 0; cb < CW; cb += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + half * CW + cb, acc);
+        tmem_ld_wait();
+        const double2* cst = sCst + half * CW + cb;
+        if (p.mode == HAWQ_EPI_REQUANT) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 16) {
+            uint32_t w[4];
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              uint32_t packed = 0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const double2 cm = cst[j + g4 * 4 + k];
+                const double d = __hiloint2double(0x43300000, acc[j + g4 * 4 + k] ^ 0x80000000) - cm.x;
+                const int q = clampi(__double2loint(__fma_rn(d, cm.y, kMagic)), q_lo, q_hi);
+                packed |= (uint32_t)(q & 0xFF) << (8 * k);
+              }
+              w[g4] = packed;
+            }
+            *reinterpret_cast<uint4*>(mylow + cb + j) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        } else if (p.mode == HAWQ_EPI_RAW_I32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            int4 o;
+            o.x = (int)acc[j + 0] + (int)(kOffS - cst[j + 0].x);
+            o.y = (int)acc[j + 1] + (int)(kOffS - cst[j + 1].x);
+            o.z = (int)acc[j + 2] + (int)(kOffS - cst[j + 2].x);
+            o.w = (int)acc[j + 3] + (int)(kOffS - cst[j + 3].x);
+            *reinterpret_cast<int4*>(myrow + (cb + j) * 4) = o;
+          }
+        } else {   // RESIDUAL: groups of 8 channels (one 16-byte vector of uint16 residuals / two of int32)
+#pragma unroll
+          for (int j = 0; j < 32; j += 16) {
+            uint32_t lw[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int jj = j + h * 8;
+              int r[8];
+              if (res_es == 2) {
+                const uint4 pr = *reinterpret_cast<const uint4*>(myrow + (cb + jj) * 2);
+                r[0] = pr.x & 0xFFFF; r[1] = pr.x >> 16; r[2] = pr.y & 0xFFFF; r[3] = pr.y >> 16;
+                r[4] = pr.z & 0xFFFF; r[5] = pr.z >> 16; r[6] = pr.w & 0xFFFF; r[7] = pr.w >> 16;
+              } else {
+                const int4 pa = *reinterpret_cast<const int4*>(myrow + (cb + jj) * 4);
+                const int4 pb = *reinterpret_cast<const int4*>(myrow + (cb + jj) * 4 + 16);
+                r[0] = pa.x; r[1] = pa.y; r[2] = pa.z; r[3] = pa.w; r[4] = pb.x; r[5] = pb.y; r[6] = pb.z; r[7] = pb.w;
+              }
+              int y[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const double2 cm = cst[jj + k];
+                const double d = __hiloint2double(0x43300000, acc[jj + k] ^ 0x80000000) - cm.x;
+                const int v = __double2loint(__fma_rn(d, cm.y, kMagic));
+                const double rM = (p.res_kind == 1) ? sM1[half * CW + cb + jj + k] : res_M;
+                const double dr = (res_es == 2) ? (__hiloint2double(0x43300000, r[k]) - kOffU)
+                                                : (__hiloint2double(0x43300000, r[k] ^ 0x80000000) - kOffS);
+                y[k] = max(sat_add(__double2loint(__fma_rn(dr, rM, kMagic)), v), relu_floor);
+              }
+              if (low_bits) {
+#pragma unroll
+                for (int g4 = 0; g4 < 2; ++g4) {
+                  uint32_t packed = 0;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const double dl = __hiloint2double(0x43300000, y[g4 * 4 + k] ^ 0x80000000) - kOffS;
+                    const int q = clampi(__double2loint(__fma_rn(dl, low_M, kMagic)), q_lo, q_hi);
+                    packed |= (uint32_t)(q & 0xFF) << (8 * k);
+                  }
+                  lw[h * 2 + g4] = packed;
+                }
+              }
+              if (y_es == 2) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) ymax = max(ymax, y[k]);
+                uint4 o;
+                o.x = (uint32_t)min(y[0], 65535) | ((uint32_t)min(y[1], 65535) << 16);
+                o.y = (uint32_t)min(y[2], 65535) | ((uint32_t)min(y[3], 65535) << 16);
+                o.z = (uint32_t)min(y[4], 65535) | ((uint32_t)min(y[5], 65535) << 16);
+                o.w = (uint32_t)min(y[6], 65535) | ((uint32_t)min(y[7], 65535) << 16);
+                *reinterpret_cast<uint4*>(myrow + (cb + jj) * 2) = o;   // in place: never ahead of the reads (2 B <= res_es)
+              } else if (y_es == 4) {
+                *reinterpret_cast<int4*>(myrow + (cb + jj) * 4) = make_int4(y[0], y[1], y[2], y[3]);
+                *reinterpret_cast<int4*>(myrow + (cb + jj) * 4 + 16) = make_int4(y[4], y[5], y[6], y[7]);
+              }
+            }
+            if (low_bits) *reinterpret_cast<uint4*>(mylow + cb + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+      // accumulator buffer fully read: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+
+      // coalesced copy-out of the staged outputs (rows of this warp's lane quarter, its CW columns)
+      if (y_es) {
+        const int cpr = CW * y_es / 16;
+        uint8_t* gy = reinterpret_cast<uint8_t*>(p.out);
+        for (int id = lane; id < 32 * cpr; id += 32) {
+          const int rr = id / cpr, j = id - rr * cpr;
+          const int gm = m0 + quarter * 32 + rr;
+          if (gm < p.M)
+            *reinterpret_cast<int4*>(gy + ((size_t)gm * p.Cout + c0) * y_es + j * 16) =
+                *reinterpret_cast<const int4*>(slice + rr * slice_pitch + j * 16);
+        }
+      }
+      if (low_bits) {
+        uint8_t* gl = reinterpret_cast<uint8_t*>(is_res ? p.out_low : p.out);
+        if (low_bits == 8) {
+          constexpr int cpr = CW / 16;
+          for (int id = lane; id < 32 * cpr; id += 32) {
+            const int rr = id / cpr, j = id - rr * cpr;
+            const int gm = m0 + quarter * 32 + rr;
+            if (gm < p.M)
+              *reinterpret_cast<int4*>(gl + (size_t)gm * p.Cout + c0 + j * 16) =
+                  *reinterpret_cast<const int4*>(lowslice + rr * S::LOW_PITCH + j * 16);
+          }
+        } else {   // 4-bit: 32 channels -> 16 packed bytes
+          constexpr int cpr = CW / 32;
+          for (int id = lane; id < 32 * cpr; id += 32) {
+            const int rr = id / cpr, j = id - rr * cpr;
+            const int gm = m0 + quarter * 32 + rr;
+            if (gm < p.M) {
+              const uint4 a = *reinterpret_cast<const uint4*>(lowslice + rr * S::LOW_PITCH + j * 32);
+              const uint4 b = *reinterpret_cast<const uint4*>(lowslice + rr * S::LOW_PITCH + j * 32 + 16);
+              uint4 o;
+              o.x = pack_nibbles8(a.x, a.y); o.y = pack_nibbles8(a.z, a.w);
+              o.z = pack_nibbles8(b.x, b.y); o.w = pack_nibbles8(b.z, b.w);
+              *reinterpret_cast<uint4*>(gl + (((size_t)gm * p.Cout + c0 + j * 32) >> 1)) = o;
+            }
+          }
+        }
+      }
+      __syncwarp();   // slices are reused by the next tile
+    }
+    if (is_res && p.y_bits == 16 && ymax > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
+    if (bad) atomicOr(p.status, HAWQ_FLAG_BAD_RATIO);
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace hawq

@@ -91,8 +91,11 @@ class CompiledModel:
     def __call__(self, x=None):
         """Exact forward: replays the fast graph, checks the overflow flag, falls back to int32 residuals if needed."""
         out = self.run_async(x)
+        flags = int(self.flag.item())
+        if flags & 2:
+            raise RuntimeError("hawq_b200: HAWQ_FLAG_BAD_RATIO raised (a dyadic ratio > 1 reached the fast kernel): results invalid")
         if self.residual_bits == 16:
-            if int(self.flag.item()) & 1:
+            if flags & 1:
                 self.fallbacks += 1
                 if 32 not in self.outs:
                     with torch.no_grad():

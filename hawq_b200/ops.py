@@ -96,9 +96,20 @@ def conv_desc(N, H, W, Cin, Cout, kh, kw, stride, pad, a_bits):
 
 
 def epilogue(mode, relu=0, out_bits=0, clamp=(0, 0), res_kind=0, res_bits=0, res_me=(0, 1), y_bits=0, low_bits=0,
-             low_me=(0, 1), low_clamp=(0, 0), cout_store=0):
+             low_me=(0, 1), low_clamp=(0, 0), cout_store=0, flags=0):
     return hawq_epilogue_desc(mode, int(relu), out_bits, clamp[0], clamp[1], res_kind, res_bits, res_me[0], res_me[1],
-                              y_bits, low_bits, low_me[0], low_me[1], low_clamp[0], low_clamp[1], cout_store)
+                              y_bits, low_bits, low_me[0], low_me[1], low_clamp[0], low_clamp[1], cout_store, flags)
+
+
+def ratios_le_one(*pairs):
+    """True when every (m, e) pair (or (m list, e list)) has ratio m * 2^-e <= 1: the HAWQ_EP_RATIOS_LE_ONE promise."""
+    for m, e in pairs:
+        ms = m if isinstance(m, (list, tuple)) else [m]
+        es = e if isinstance(e, (list, tuple)) else [e]
+        for mi, ei in zip(ms, es):
+            if not (mi == 0 or ei >= 31):
+                return False
+    return True
 
 
 def conv2d(x, desc, ep, w, chan, res=None, res_chan=None, fscale=None, out=None, out_low=None):

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import ops, quant_math as qmath
-from ._lib import EPI_DEQUANT_F32, EPI_RAW_I32, EPI_REQUANT, EPI_RESIDUAL
+from ._lib import EPI_DEQUANT_F32, EPI_RAW_I32, EPI_REQUANT, EPI_RESIDUAL, EP_RATIOS_LE_ONE
 
 
 class EngineConfig:
@@ -310,7 +310,8 @@ def _conv_case0(n, act, device):
     bits = act.activation_bit
     lo, hi = _act_clamp(act)
     out = _alloc(device, nb * ho * wo * ent["cout"], bits)
-    ep = ops.epilogue(EPI_REQUANT, relu=n.relu, out_bits=bits, clamp=(lo, hi))
+    ep = ops.epilogue(EPI_REQUANT, relu=n.relu, out_bits=bits, clamp=(lo, hi),
+                      flags=EP_RATIOS_LE_ONE if ops.ratios_le_one((m, e)) else 0)
     _launch_conv(n, ent, ep, chan, device, out=out)
     return Node("int", (nb, ent["cout"], ho, wo), data=out, bits=bits, signed=(act.quant_mode == "symmetric"))
 
@@ -322,7 +323,7 @@ def _conv_raw(n, device):
     chan = _chan_tensor(ent, "raw", [0] * ent["cout"], [1] * ent["cout"], device)
     nb, _, _, ho, wo = _conv_out_hw(n, ent)
     out = _alloc(device, nb * ho * wo * ent["cout"], 32)
-    _launch_conv(n, ent, ops.epilogue(EPI_RAW_I32), chan, device, out=out)
+    _launch_conv(n, ent, ops.epilogue(EPI_RAW_I32, flags=EP_RATIOS_LE_ONE), chan, device, out=out)
     return out, ent
 
 
@@ -336,11 +337,13 @@ def _launch_residual(r, low_act, device):
     m2, e2 = _dyadic(act, a_sf, w_sf, "case1-main")
     chan = _chan_tensor(ent, _act_tag("c1", act), m2, e2, device)
     res_chan = None
+    pairs = [(m2, e2)]
     if ident.kind == "conv":
         res, ient = _conv_raw(ident, device)
         m1, e1 = _dyadic(act, id_sf, id_w_sf, "case1-idconv")
         res_chan = _chan_tensor(ient, _act_tag("c1res", act), m1, e1, device)
         res_kind, res_bits, res_me = 1, 32, (0, 1)
+        pairs.append((m1, e1))
     else:
         ident = materialize(ident, device)
         if ident.bits not in (16, 32):
@@ -348,6 +351,7 @@ def _launch_residual(r, low_act, device):
         res = ident.data
         m1, e1 = _dyadic(act, id_sf, id_w_sf, "case1-id")
         res_kind, res_bits, res_me = 0, ident.bits, (m1[0], e1[0])
+        pairs.append((m1[0], e1[0]))
     nb, _, _, ho, wo = _conv_out_hw(conv, ent)
     numel = nb * ho * wo * ent["cout"]
     y_bits = config.residual_bits if r.relu else 32
@@ -360,9 +364,11 @@ def _launch_residual(r, low_act, device):
         lo, hi = _act_clamp(low_act)
         low = _alloc(device, numel, low_act.activation_bit)
         kw = dict(low_bits=low_act.activation_bit, low_me=(lm[0], le[0]), low_clamp=(lo, hi))
+        pairs.append((lm[0], le[0]))
         low_node = Node("int", (nb, ent["cout"], ho, wo), data=low, bits=low_act.activation_bit,
                         signed=(low_act.quant_mode == "symmetric"))
-    ep = ops.epilogue(EPI_RESIDUAL, relu=r.relu, res_kind=res_kind, res_bits=res_bits, res_me=res_me, y_bits=y_bits, **kw)
+    ep = ops.epilogue(EPI_RESIDUAL, relu=r.relu, res_kind=res_kind, res_bits=res_bits, res_me=res_me, y_bits=y_bits,
+                      flags=EP_RATIOS_LE_ONE if ops.ratios_le_one(*pairs) else 0, **kw)
     _launch_conv(conv, ent, ep, chan, device, out=y, out_low=low, res=res, res_chan=res_chan)
     r.shape = (nb, ent["cout"], ho, wo)
     r.become_int(y, y_bits, signed=(y_bits == 32))

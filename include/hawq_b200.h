@@ -47,6 +47,7 @@ enum hawq_status {
 
 /* bits of the device status word */
 #define HAWQ_FLAG_RESIDUAL_OVERFLOW 1   /* a post-ReLU residual value exceeded 65535 while stored as uint16 */
+#define HAWQ_FLAG_BAD_RATIO 2           /* HAWQ_EP_RATIOS_LE_ONE was promised but a ratio > 1 was found: results invalid */
 
 /* Per-output-channel epilogue parameters (16 B, one vector load per channel).
  * bias = bias_integer (quant_modules.py:481-484), (m, e) = batch_frexp of the requant ratio of that channel. */
@@ -91,7 +92,13 @@ typedef struct {
   int32_t low_lo, low_hi;
   /* DEQUANT_F32 */
   int32_t cout_store;     /* number of real output columns (<= Cout), row pitch of the fp32 output */
+  int32_t flags;          /* HAWQ_EP_*: promises of the caller that unlock faster kernels */
 } hawq_epilogue_desc;
+
+/* Caller promise: every dyadic pair of this launch (chan[], res_chan[], res_m/e, low_m/e) has ratio m * 2^-e <= 1, i.e.
+ * e >= 31 or m == 0 (true for every HAWQ ResNet layer).  Enables the tcgen05 kernel, which evaluates RHE(v * m / 2^e) with one
+ * exact FP64 FMA.  The kernel re-checks the promise and raises HAWQ_FLAG_BAD_RATIO instead of computing wrong numbers. */
+#define HAWQ_EP_RATIOS_LE_ONE 1
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
 int hawq_abi_version(void);

@@ -58,9 +58,13 @@ CONV_GEOMS = [
 ]
 
 
+TC_FLAG = 1   # HAWQ_EP_RATIOS_LE_ONE: routes int8 convolutions to the tcgen05 kernel
+
+
+@pytest.mark.parametrize("tc", [0, 1])
 @pytest.mark.parametrize("a_bits", [8, 4])
 @pytest.mark.parametrize("geom", CONV_GEOMS)
-def test_conv_requant(geom, a_bits):
+def test_conv_requant(geom, a_bits, tc):
     n, h, w, cin, cout, k, s, p = geom
     r = rng(sum(v * (i + 3) for i, v in enumerate(geom)) * 8 + a_bits)
     ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
@@ -71,9 +75,9 @@ def test_conv_requant(geom, a_bits):
     for out_bits, clamp, relu in [(8, (-128, 127), 1), (4, (0, 15), 1), (16, (-32768, 32767), 0), (32, (-2 ** 31, 2 ** 31 - 1), 0)]:
         chan = make_chan(r, cout, ratio_lo=1e-5 if out_bits <= 8 else 1e-3)
         d = ops.conv_desc(n, h, w, cin, cout, k, k, s, p, a_bits)
-        ep = ops.epilogue(EPI_REQUANT, relu=relu, out_bits=out_bits, clamp=clamp)
+        ep = ops.epilogue(EPI_REQUANT, relu=relu, out_bits=out_bits, clamp=clamp, flags=TC_FLAG * tc)
         (c_out,), (g_out,) = run_both("conv2d", dict(x=x, desc=d, ep=ep, w=wt, chan=chan, out=out_buf(n * ho * wo * cout, out_bits)), ["out"])
-        assert torch.equal(c_out, g_out), (geom, a_bits, out_bits)
+        assert torch.equal(c_out, g_out), (geom, a_bits, out_bits, tc)
 
 
 @pytest.mark.parametrize("ratio_kind", ["pow2_ties", "above_one_mixed"])
@@ -109,9 +113,10 @@ def test_conv_requant_ties_and_generic_path(ratio_kind):
         assert torch.equal(a, b), ratio_kind
 
 
+@pytest.mark.parametrize("tc", [0, 1])
 @pytest.mark.parametrize("a_bits", [8, 4])
 @pytest.mark.parametrize("geom", CONV_GEOMS[:4])
-def test_conv_residual(geom, a_bits):
+def test_conv_residual(geom, a_bits, tc):
     n, h, w, cin, cout, k, s, p = geom
     r = rng(sum(v * (i + 5) for i, v in enumerate(geom)) * 8 + a_bits + 1)
     ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
@@ -129,13 +134,13 @@ def test_conv_residual(geom, a_bits):
         res_chan = make_chan(r, cout, ratio_lo=1e-2, ratio_hi=0.9) if res_kind == 1 else None
         res_me = dyadic(0.37)
         ep = ops.epilogue(EPI_RESIDUAL, relu=relu, res_kind=res_kind, res_bits=res_bits, res_me=res_me, y_bits=y_bits,
-                          low_bits=low_bits, low_me=low_me, low_clamp=(0, 15) if low_bits == 4 else (-128, 127))
+                          low_bits=low_bits, low_me=low_me, low_clamp=(0, 15) if low_bits == 4 else (-128, 127), flags=TC_FLAG * tc)
         args = dict(x=x, desc=d, ep=ep, w=wt, chan=chan, res=res, res_chan=res_chan,
                     out=out_buf(numel, y_bits) if y_bits else None, out_low=out_buf(numel, low_bits) if low_bits else None)
         keys = [k_ for k_ in ("out", "out_low") if args[k_] is not None]
         c_outs, g_outs = run_both("conv2d", args, keys)
         for a, b, k_ in zip(c_outs, g_outs, keys):
-            assert torch.equal(a, b), (geom, a_bits, res_kind, res_bits, y_bits, low_bits, k_)
+            assert torch.equal(a, b), (geom, a_bits, res_kind, res_bits, y_bits, low_bits, k_, tc)
 
 
 def test_residual_overflow_flag():
@@ -164,9 +169,10 @@ def test_conv_raw_and_dequant():
     wt = torch.from_numpy(r.randint(-128, 128, size=(cout, k, k, cin)).astype(np.int8))
     chan = make_chan(r, cout)
     d = ops.conv_desc(n, h, w, cin, cout, k, k, s, p, 8)
-    (c,), (g,) = run_both("conv2d", dict(x=x, desc=d, ep=ops.epilogue(EPI_RAW_I32), w=wt, chan=chan,
-                                         out=out_buf(n * ho * wo * cout, 32)), ["out"])
-    assert torch.equal(c, g)
+    for tc in (0, 1):
+        (c,), (g,) = run_both("conv2d", dict(x=x, desc=d, ep=ops.epilogue(EPI_RAW_I32, flags=TC_FLAG * tc), w=wt, chan=chan,
+                                             out=out_buf(n * ho * wo * cout, 32)), ["out"])
+        assert torch.equal(c, g), tc
     # linear tail: 1000 classes padded to 1024
     nb, kk, co, cp = 5, 512, 1000, 1024
     xl = rand_act(r, nb * kk, 8)

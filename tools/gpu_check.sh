@@ -20,8 +20,10 @@ if [[ $what == bench || $what == all ]]; then
   done
 fi
 if [[ $what == quick ]]; then
-  timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_network_gpu.py -m gpu -x -q -p no:cacheprovider -k "not every_activation" > gpurun_out/pytest_gpu.log 2>&1
-  echo "pytest exit $?"; tail -5 gpurun_out/pytest_gpu.log
+  timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider > gpurun_out/pytest_kernels.log 2>&1
+  echo "pytest kernels exit $?"; tail -12 gpurun_out/pytest_kernels.log
+  timeout 900 python -m pytest tests/test_network_gpu.py -m gpu -x -q -p no:cacheprovider -k "not every_activation" > gpurun_out/pytest_gpu.log 2>&1
+  echo "pytest network exit $?"; tail -5 gpurun_out/pytest_gpu.log
   for cfg in ${CFGS:-resnet50:uniform8}; do
     set -- ${cfg/:/ }
     timeout 600 python bench.py --arch $1 --scheme $2 --steps 20 --warmup 5 --no-cpu-baseline --detail gpurun_out/detail_$1_$2.json > gpurun_out/bench_$1_$2.json 2> gpurun_out/bench_$1_$2.err
