@@ -65,6 +65,19 @@ static int set_conv_attr() {
   return HAWQ_OK;
 }
 
+template <int EPI>
+static int set_tc_attr() {
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, EPI>::TOTAL));
+  return HAWQ_OK;
+}
+
+template <int EPI>
+static void launch_tc(const ConvParams& p, bool wide, int grid, cudaStream_t st) {
+  if (wide) conv_tc_kernel<128, EPI><<<grid, TC_THREADS, TcSmem<128, EPI>::TOTAL, st>>>(p);
+  else conv_tc_kernel<64, EPI><<<grid, TC_THREADS, TcSmem<64, EPI>::TOTAL, st>>>(p);
+}
+
 template <int BN, bool A4>
 static void launch_conv(const ConvParams& p, dim3 grid, cudaStream_t s) {
   const int smem = ConvSmem<BN, A4>::TOTAL;
@@ -91,8 +104,9 @@ int hawq_create(int device, hawq_handle** out) {
   CUDA_TRY(cudaMalloc(&h->status, sizeof(int32_t)));
   CUDA_TRY(cudaMemset(h->status, 0, sizeof(int32_t)));
   int rc;
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::TOTAL));
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::TOTAL));
+  if ((rc = set_tc_attr<TC_EPI_REQ>()) || (rc = set_tc_attr<TC_EPI_RAW>()) || (rc = set_tc_attr<TC_EPI_RES22>()) ||
+      (rc = set_tc_attr<TC_EPI_RES44>()) || (rc = set_tc_attr<TC_EPI_RES42>()))
+    return rc;
   if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
       (rc = set_conv_attr<64, true>()))
     return rc;
@@ -206,17 +220,26 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
 
   // tcgen05 path: int8 activations, the three hot epilogues, all ratios <= 1 (promised), HAWQ_B200_TC != 0
   static const bool tc_enabled = [] { const char* e = getenv("HAWQ_B200_TC"); return !(e && e[0] == '0'); }();
-  const bool tc_epi = (ep->mode == HAWQ_EPI_REQUANT && ep->out_bits <= 8) || ep->mode == HAWQ_EPI_RESIDUAL || ep->mode == HAWQ_EPI_RAW_I32;
+  const bool tc_epi = (ep->mode == HAWQ_EPI_REQUANT && ep->out_bits <= 8) || (ep->mode == HAWQ_EPI_RESIDUAL && ep->y_bits != 0) ||
+                      ep->mode == HAWQ_EPI_RAW_I32;
   if (tc_enabled && d->a_bits == 8 && tc_epi && (ep->flags & HAWQ_EP_RATIOS_LE_ONE) && !p.slow_scalar) {
     const bool wide = (d->Cout % 128 == 0);
     const long long tiles = ((M + TC_BM - 1) / TC_BM) * (d->Cout / (wide ? 128 : 64));
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
     cudaStream_t st = (cudaStream_t)stream;
-    if (wide) conv_tc_kernel<128><<<grid, TC_THREADS, TcSmem<128>::TOTAL, st>>>(p);
-    else conv_tc_kernel<64><<<grid, TC_THREADS, TcSmem<64>::TOTAL, st>>>(p);
+    if (ep->mode == HAWQ_EPI_REQUANT) launch_tc<TC_EPI_REQ>(p, wide, grid, st);
+    else if (ep->mode == HAWQ_EPI_RAW_I32) launch_tc<TC_EPI_RAW>(p, wide, grid, st);
+    else {
+      const int res_es = (ep->res_kind == 1 || ep->res_bits == 32) ? 4 : 2;
+      if (res_es == 2 && ep->y_bits == 16) launch_tc<TC_EPI_RES22>(p, wide, grid, st);
+      else if (res_es == 4 && ep->y_bits == 32) launch_tc<TC_EPI_RES44>(p, wide, grid, st);
+      else if (res_es == 4 && ep->y_bits == 16) launch_tc<TC_EPI_RES42>(p, wide, grid, st);
+      else goto legacy;   // uint16 residual in, int32 out: not a combination the engine produces
+    }
     return launch_check("conv_tc");
   }
 
+legacy:
   const bool bn128 = (d->Cout % 128 == 0);
   const dim3 grid((unsigned)((M + CONV_BM - 1) / CONV_BM), (unsigned)(d->Cout / (bn128 ? 128 : 64)), 1);
   cudaStream_t s = (cudaStream_t)stream;

@@ -30,23 +30,35 @@ constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_MMA_WARP = TC_PRODUCER_WARPS;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + TC_EPI_WARPS) * 32;   // 416
 
-template <int BN>
+// epilogue variants (compile-time): element sizes of the residual operand read into / the output staged in the slice
+constexpr int TC_EPI_REQ = 0;      // REQUANT -> 4/8 bit
+constexpr int TC_EPI_RAW = 1;      // RAW_I32
+constexpr int TC_EPI_RES22 = 2;    // RESIDUAL: uint16 stream in, uint16 stream out
+constexpr int TC_EPI_RES44 = 3;    // RESIDUAL: int32 in (stream or identity-conv accumulator), int32 out
+constexpr int TC_EPI_RES42 = 4;    // RESIDUAL: int32 in, uint16 out
+
+template <int BN, int EPI>
 struct TcSmem {
   static constexpr int A_STAGE = TC_BM * 64;
   static constexpr int B_STAGE = BN * 64;
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int RING = TC_STAGES * STAGE;
-  static constexpr int COLS_PER_WARP = BN / 2;
-  static constexpr int SLICE_PITCH = COLS_PER_WARP * 4 + 16;              // worst case int32 + 16 B pad (conflict-free)
-  static constexpr int SLICE = 32 * SLICE_PITCH;
-  static constexpr int LOW_PITCH = COLS_PER_WARP + 16;
+  static constexpr int CW = BN / 2;                                        // columns per epilogue warp
+  static constexpr int RES_ES = (EPI == TC_EPI_RES22) ? 2 : (EPI >= TC_EPI_RES44 ? 4 : 0);
+  static constexpr int Y_ES = (EPI == TC_EPI_RES22 || EPI == TC_EPI_RES42) ? 2 : ((EPI == TC_EPI_RES44 || EPI == TC_EPI_RAW) ? 4 : 0);
+  static constexpr int SLICE_ES = RES_ES > Y_ES ? RES_ES : Y_ES;
+  static constexpr int SLICE_PITCH = CW * SLICE_ES + 16;                   // +16 B: 16-byte row-per-lane accesses conflict-free
+  static constexpr int SLICE = SLICE_ES ? 32 * SLICE_PITCH : 0;
+  static constexpr int SLICE_BUFS = (EPI == TC_EPI_RES22) ? 2 : 1;         // uint16 residual tiles are prefetched one tile ahead
+  static constexpr int LOW_PITCH = CW + 16;
   static constexpr int LOW_SLICE = 32 * LOW_PITCH;
   static constexpr int SLICES_OFF = RING;
-  static constexpr int LOW_OFF = SLICES_OFF + TC_EPI_WARPS * SLICE;
-  static constexpr int CST_OFF = LOW_OFF + TC_EPI_WARPS * LOW_SLICE;      // double2 {Cb, M}[BN]
-  static constexpr int M1_OFF = CST_OFF + BN * 16;                        // double M1[BN]
-  static constexpr int BAR_OFF = M1_OFF + BN * 8;                         // mbarriers + tmem base
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;                      // + slack for 1024 B alignment of the ring
+  static constexpr int LOW_OFF = SLICES_OFF + TC_EPI_WARPS * SLICE * SLICE_BUFS;
+  static constexpr int CST_OFF = LOW_OFF + TC_EPI_WARPS * LOW_SLICE;       // double2 {Cb, M}[BN]
+  static constexpr int M1_OFF = CST_OFF + BN * 16;                         // double M1[BN]
+  static constexpr int BAR_OFF = M1_OFF + BN * 8;                          // mbarriers + tmem base
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;                       // + slack for 1024 B alignment of the ring
+  static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -60,7 +72,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -69,7 +81,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // bounded wait: a broken pipeline protocol becomes a trap (cudaErrorLaunchFailure), never a hung GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t i = 0; i < 20000000u; ++i)
+  for (uint32_t i = 0; i < 4000000u; ++i)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
 }
@@ -134,15 +146,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n, bool a_signed
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams p) {
-  using S = TcSmem<BN>;
+  using S = TcSmem<BN, EPI>;
   constexpr int BM = TC_BM, STAGES = TC_STAGES;
-  constexpr int CW = S::COLS_PER_WARP;           // columns handled by one epilogue warp: 32 or 64
+  constexpr int CW = S::CW;                      // columns handled by one epilogue warp: 32 or 64
   constexpr int TMEM_COLS = 2 * BN;              // two accumulator buffers (power of two >= 32: 128 / 256)
+  constexpr int RES_ES = S::RES_ES, Y_ES = S::Y_ES, PITCH = S::SLICE_PITCH;
+  constexpr bool IS_RES = EPI >= TC_EPI_RES22;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps shared-space provenance
   const uint32_t smem_base = smem_u32(smem);
   double2* sCst = reinterpret_cast<double2*>(smem + S::CST_OFF);
   double* sM1 = reinterpret_cast<double*>(smem + S::M1_OFF);
@@ -179,6 +193,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   if (warp < TC_PRODUCER_WARPS) {
     // =============================================================================== producers (128 threads)
     const int row = tid;                       // A row of the tile owned by this thread
+    const uint32_t a_off = swz<64>(row, 0) & ~63u;                 // row base; chunk c lives at a_off + ((c ^ sw) << 4)
+    const uint32_t a_sw = (row >> 1) & 3;
     uint32_t it = 0;                           // global k-tile counter (ring position)
     uint32_t pending = 0;                      // k-tiles issued but not yet signalled
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -190,6 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       const int r = mm - n * (p.Ho * p.Wo);
       const int ho = r / p.Wo, wo = r - ho * p.Wo;
       const int hi0 = ho * p.stride - p.pad, wi0 = wo * p.stride - p.pad, pix = n * p.H * p.W;
+      const int8_t* wrow = p.w + (size_t)n0 * p.K;
       int c = 0, kw = 0, kh = 0;
       for (int kt = 0; kt < KT; ++kt, ++it) {
         const int stage = it % STAGES;
@@ -200,14 +217,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
           const int hi = hi0 + kh, wi = wi0 + kw;
           const bool v = a_ok && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W;
           const uint8_t* src = v ? p.x + (size_t)(pix + hi * p.W + wi) * p.x_pix_bytes + c * 64 : p.x;
+          const int nb = v ? 16 : 0;
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) cp_async_16(a_base + swz<64>(row, ch), src + ch * 16, v ? 16 : 0);
+          for (int ch = 0; ch < 4; ++ch) cp_async_16(a_base + a_off + ((ch ^ a_sw) << 4), src + ch * 16, nb);
         }
 #pragma unroll
         for (int i = 0; i < BN / 32; ++i) {     // B: BN rows x 4 chunks over 128 threads
           const int id = tid + i * 128;
           const int brow = id >> 2, ch = id & 3;
-          cp_async_16(b_base + swz<64>(brow, ch), p.w + (size_t)(n0 + brow) * p.K + kt * 64 + ch * 16, 16);
+          cp_async_16(b_base + swz<64>(brow, ch), wrow + (size_t)brow * p.K + kt * 64 + ch * 16, 16);
         }
         cp_async_commit();
         ++pending;
@@ -225,19 +243,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     fence_proxy_async();
     for (uint32_t j = pending; j > 0; --j) mbar_arrive(full_bar((it - j) % STAGES));
   } else if (warp == TC_MMA_WARP) {
-    // =============================================================================== MMA issuer
-    const uint32_t idesc = umma_idesc_i8(BM, BN, true);
-    uint32_t it = 0, tile_iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
-      const int buf = tile_iter & 1;
-      mbar_wait(tempty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * BN;
-      for (int kt = 0; kt < KT; ++kt, ++it) {
-        const int stage = it % STAGES;
-        mbar_wait(full_bar(stage), (it / STAGES) & 1);
+    // =============================================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_i8(BM, BN, true);
+      uint32_t it = 0, tile_iter = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+        const int buf = tile_iter & 1;
+        mbar_wait(tempty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+          const int stage = it % STAGES;
+          mbar_wait(full_bar(stage), (it / STAGES) & 1);
+          tc_fence_after();
           const uint32_t a_addr = smem_base + stage * S::STAGE;
           const uint32_t b_addr = a_addr + S::A_STAGE;
 #pragma unroll
@@ -246,7 +264,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
           umma_commit(empty_bar(stage));                          // smem stage reusable once these MMAs retire
           if (kt == KT - 1) umma_commit(tfull_bar(buf));          // accumulator complete
         }
-        __syncwarp();
       }
     }
   } else {
@@ -254,99 +271,117 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     const int ew = warp - (TC_MMA_WARP + 1);     // 0..7
     const int quarter = warp & 3;                // TMEM lane quarter this warp may access
     const int half = ew >> 2;                    // column half
-    const int row = quarter * 32 + lane;         // tile row owned by this thread
-    uint8_t* slice = smem + S::SLICES_OFF + ew * S::SLICE;
+    uint8_t* slice0 = smem + S::SLICES_OFF + ew * S::SLICE * S::SLICE_BUFS;
     uint8_t* lowslice = smem + S::LOW_OFF + ew * S::LOW_SLICE;
-    const bool is_res = p.mode == HAWQ_EPI_RESIDUAL;
-    const int res_es = is_res ? ((p.res_kind == 1 || p.res_bits == 32) ? 4 : 2) : 0;
-    const int y_es = is_res ? p.y_bits / 8 : (p.mode == HAWQ_EPI_RAW_I32 ? 4 : 0);   // bytes per element staged in `slice`
-    const int slice_pitch = CW * (res_es > y_es ? res_es : y_es) + 16;
-    const int low_bits = is_res ? p.low_bits : (p.mode == HAWQ_EPI_REQUANT ? p.out_bits : 0);
-    const double res_M = dyadic_to_double(p.res_m, p.res_e), low_M = dyadic_to_double(p.low_m, p.low_e);
+    uint8_t* mylow = lowslice + lane * S::LOW_PITCH;
+    const int low_bits = IS_RES ? p.low_bits : (EPI == TC_EPI_REQ ? p.out_bits : 0);
+    const double low_M = dyadic_to_double(p.low_m, p.low_e);
     const int relu_floor = p.relu ? 0 : (int)0x80000000;
-    const int q_lo = (p.mode == HAWQ_EPI_REQUANT) ? (p.relu ? max(p.lo, 0) : p.lo) : p.low_lo;
-    const int q_hi = (p.mode == HAWQ_EPI_REQUANT) ? p.hi : p.low_hi;
+    const int q_lo = (EPI == TC_EPI_REQ) ? (p.relu ? max(p.lo, 0) : p.lo) : p.low_lo;
+    const int q_hi = (EPI == TC_EPI_REQ) ? p.hi : p.low_hi;
     constexpr double kMagic = 6755399441055744.0, kOffS = 4503601774854144.0, kOffU = 4503599627370496.0;
+    constexpr int RES_CPR = CW * RES_ES / 16;    // 16-byte chunks per residual row
     int ymax = 0, bad = 0;
     int cur_n0 = -1;
     uint32_t tile_iter = 0;
+
+    auto prefetch_residual = [&](int tile, uint8_t* dst) {
+      if constexpr (IS_RES) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        const uint8_t* gres = reinterpret_cast<const uint8_t*>(p.res) + ((size_t)(m0 + quarter * 32) * p.Cout + n0 + half * CW) * RES_ES;
+        const int rows_ok = p.M - (m0 + quarter * 32);
+#pragma unroll
+        for (int i = 0; i < RES_CPR; ++i) {       // 32 rows x RES_CPR chunks, a warp instruction covers whole rows
+          const int id = lane + i * 32;
+          const int rr = id / RES_CPR, j = id % RES_CPR;
+          const bool v = rr < rows_ok;
+          cp_async_16(smem_u32(dst + rr * PITCH + j * 16), v ? gres + (size_t)rr * p.Cout * RES_ES + j * 16 : gres, v ? 16 : 0);
+        }
+      }
+      cp_async_commit();
+    };
+
+    if constexpr (S::SLICE_BUFS == 2) {
+      if ((int)blockIdx.x < num_tiles) prefetch_residual(blockIdx.x, slice0);
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       const int buf = tile_iter & 1;
       const int c0 = n0 + half * CW;             // first global channel of this warp
+      uint8_t* slice = slice0 + (S::SLICE_BUFS == 2 ? (tile_iter & 1) * S::SLICE : 0);
 
-      // per-channel constants of this tile's channel block (shared by the 8 epilogue warps; warp ew loads BN/8)
+      // per-channel constants of this tile's channel block (shared by the 8 epilogue warps)
       if (n0 != cur_n0) {
         asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32));     // everyone finished reading the previous block
         for (int i = tid - (TC_MMA_WARP + 1) * 32; i < BN; i += TC_EPI_WARPS * 32) {
           const hawq_chan ch = p.chan[n0 + i];
           sCst[i] = make_double2(kOffS - (double)ch.bias, dyadic_to_double(ch.m, ch.e));
           bad |= !dyadic_is_fast(ch.m, ch.e);
-          if (is_res && p.res_kind == 1) {
-            const hawq_chan rc = p.res_chan[n0 + i];
-            sM1[i] = dyadic_to_double(rc.m, rc.e);
-            bad |= !dyadic_is_fast(rc.m, rc.e);
+          if constexpr (IS_RES) {
+            if (p.res_kind == 1) {
+              const hawq_chan rc = p.res_chan[n0 + i];
+              sM1[i] = dyadic_to_double(rc.m, rc.e);
+              bad |= !dyadic_is_fast(rc.m, rc.e);
+            } else {
+              sM1[i] = dyadic_to_double(p.res_m, p.res_e);
+            }
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32));
         cur_n0 = n0;
       }
 
-      // residual slice: 32 rows x CW columns, coalesced (a warp instruction covers whole rows)
-      if (res_es) {
-        const int cpr = CW * res_es / 16;
-        const uint8_t* gres = reinterpret_cast<const uint8_t*>(p.res);
-        for (int id = lane; id < 32 * cpr; id += 32) {
-          const int rr = id / cpr, j = id - rr * cpr;
-          const int gm = m0 + quarter * 32 + rr;
-          const bool v = gm < p.M;
-          const uint8_t* src = v ? gres + ((size_t)gm * p.Cout + c0) * res_es + j * 16 : gres;
-          cp_async_16(smem_u32(slice + rr * slice_pitch + j * 16), src, v ? 16 : 0);
+      if constexpr (IS_RES) {
+        if constexpr (S::SLICE_BUFS == 2) {        // this tile's residual was prefetched; start the next one
+          const int nxt = tile + gridDim.x;
+          if (nxt < num_tiles) prefetch_residual(nxt, slice0 + ((tile_iter + 1) & 1) * S::SLICE);
+          else cp_async_commit();
+        } else {
+          prefetch_residual(tile, slice);
         }
-        cp_async_commit();
       }
 
       mbar_wait(tfull_bar(buf), (tile_iter >> 1) & 1);
       tc_fence_after();
-      if (res_es) {
-        cp_async_wait<0>();
+      if constexpr (IS_RES) {
+        if constexpr (S::SLICE_BUFS == 2) cp_async_wait<1>();
+        else cp_async_wait<0>();
         __syncwarp();
       }
-      uint8_t* myrow = slice + lane * slice_pitch;
-      uint8_t* mylow = lowslice + lane * S::LOW_PITCH;
+      uint8_t* myrow = slice + lane * PITCH;
 
-#pragma unroll 1
+#pragma unroll
       for (int cb = 0; cb < CW; cb += 32) {
         uint32_t acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + half * CW + cb, acc);
         tmem_ld_wait();
         const double2* cst = sCst + half * CW + cb;
-        if (p.mode == HAWQ_EPI_REQUANT) {
+        const double* m1 = sM1 + half * CW + cb;
+        if constexpr (EPI == TC_EPI_REQ) {
 #pragma unroll
           for (int j = 0; j < 32; j += 16) {
             uint32_t w[4];
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
-              uint32_t packed = 0;
+              int q[4];
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const double2 cm = cst[j + g4 * 4 + k];
                 const double d = __hiloint2double(0x43300000, acc[j + g4 * 4 + k] ^ 0x80000000) - cm.x;
-                const int q = clampi(__double2loint(__fma_rn(d, cm.y, kMagic)), q_lo, q_hi);
-                packed |= (uint32_t)(q & 0xFF) << (8 * k);
+                q[k] = clampi(__double2loint(__fma_rn(d, cm.y, kMagic)), q_lo, q_hi);
               }
-              w[g4] = packed;
+              w[g4] = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
             }
             *reinterpret_cast<uint4*>(mylow + cb + j) = make_uint4(w[0], w[1], w[2], w[3]);
           }
-        } else if (p.mode == HAWQ_EPI_RAW_I32) {
+        } else if constexpr (EPI == TC_EPI_RAW) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            int4 o;
-            o.x = (int)acc[j + 0] + (int)(kOffS - cst[j + 0].x);
-            o.y = (int)acc[j + 1] + (int)(kOffS - cst[j + 1].x);
-            o.z = (int)acc[j + 2] + (int)(kOffS - cst[j + 2].x);
-            o.w = (int)acc[j + 3] + (int)(kOffS - cst[j + 3].x);
+            int4 o;   // bias = kOffS - Cb (exact); the double subtraction keeps everything on the FP64 pipe
+            o.x = __double2loint((__hiloint2double(0x43300000, acc[j + 0] ^ 0x80000000) - cst[j + 0].x) + kMagic);
+            o.y = __double2loint((__hiloint2double(0x43300000, acc[j + 1] ^ 0x80000000) - cst[j + 1].x) + kMagic);
+            o.z = __double2loint((__hiloint2double(0x43300000, acc[j + 2] ^ 0x80000000) - cst[j + 2].x) + kMagic);
+            o.w = __double2loint((__hiloint2double(0x43300000, acc[j + 3] ^ 0x80000000) - cst[j + 3].x) + kMagic);
             *reinterpret_cast<int4*>(myrow + (cb + j) * 4) = o;
           }
         } else {   // RESIDUAL: groups of 8 channels (one 16-byte vector of uint16 residuals / two of int32)
@@ -357,7 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
             for (int h = 0; h < 2; ++h) {
               const int jj = j + h * 8;
               int r[8];
-              if (res_es == 2) {
+              if constexpr (RES_ES == 2) {
                 const uint4 pr = *reinterpret_cast<const uint4*>(myrow + (cb + jj) * 2);
                 r[0] = pr.x & 0xFFFF; r[1] = pr.x >> 16; r[2] = pr.y & 0xFFFF; r[3] = pr.y >> 16;
                 r[4] = pr.z & 0xFFFF; r[5] = pr.z >> 16; r[6] = pr.w & 0xFFFF; r[7] = pr.w >> 16;
@@ -372,34 +407,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
                 const double2 cm = cst[jj + k];
                 const double d = __hiloint2double(0x43300000, acc[jj + k] ^ 0x80000000) - cm.x;
                 const int v = __double2loint(__fma_rn(d, cm.y, kMagic));
-                const double rM = (p.res_kind == 1) ? sM1[half * CW + cb + jj + k] : res_M;
-                const double dr = (res_es == 2) ? (__hiloint2double(0x43300000, r[k]) - kOffU)
+                const double dr = (RES_ES == 2) ? (__hiloint2double(0x43300000, r[k]) - kOffU)
                                                 : (__hiloint2double(0x43300000, r[k] ^ 0x80000000) - kOffS);
-                y[k] = max(sat_add(__double2loint(__fma_rn(dr, rM, kMagic)), v), relu_floor);
+                y[k] = max(sat_add(__double2loint(__fma_rn(dr, m1[jj + k], kMagic)), v), relu_floor);
               }
               if (low_bits) {
 #pragma unroll
                 for (int g4 = 0; g4 < 2; ++g4) {
-                  uint32_t packed = 0;
+                  int q[4];
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
                     const double dl = __hiloint2double(0x43300000, y[g4 * 4 + k] ^ 0x80000000) - kOffS;
-                    const int q = clampi(__double2loint(__fma_rn(dl, low_M, kMagic)), q_lo, q_hi);
-                    packed |= (uint32_t)(q & 0xFF) << (8 * k);
+                    q[k] = clampi(__double2loint(__fma_rn(dl, low_M, kMagic)), q_lo, q_hi);
                   }
-                  lw[h * 2 + g4] = packed;
+                  lw[h * 2 + g4] = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
                 }
               }
-              if (y_es == 2) {
+              if constexpr (Y_ES == 2) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) ymax = max(ymax, y[k]);
                 uint4 o;
-                o.x = (uint32_t)min(y[0], 65535) | ((uint32_t)min(y[1], 65535) << 16);
-                o.y = (uint32_t)min(y[2], 65535) | ((uint32_t)min(y[3], 65535) << 16);
-                o.z = (uint32_t)min(y[4], 65535) | ((uint32_t)min(y[5], 65535) << 16);
-                o.w = (uint32_t)min(y[6], 65535) | ((uint32_t)min(y[7], 65535) << 16);
-                *reinterpret_cast<uint4*>(myrow + (cb + jj) * 2) = o;   // in place: never ahead of the reads (2 B <= res_es)
-              } else if (y_es == 4) {
+                o.x = __byte_perm(min(y[0], 65535), min(y[1], 65535), 0x5410);
+                o.y = __byte_perm(min(y[2], 65535), min(y[3], 65535), 0x5410);
+                o.z = __byte_perm(min(y[4], 65535), min(y[5], 65535), 0x5410);
+                o.w = __byte_perm(min(y[6], 65535), min(y[7], 65535), 0x5410);
+                *reinterpret_cast<uint4*>(myrow + (cb + jj) * 2) = o;   // in place: never ahead of the reads (2 B <= RES_ES)
+              } else {
                 *reinterpret_cast<int4*>(myrow + (cb + jj) * 4) = make_int4(y[0], y[1], y[2], y[3]);
                 *reinterpret_cast<int4*>(myrow + (cb + jj) * 4 + 16) = make_int4(y[4], y[5], y[6], y[7]);
               }
@@ -414,47 +447,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       if (lane == 0) mbar_arrive(tempty_bar(buf));
 
       // coalesced copy-out of the staged outputs (rows of this warp's lane quarter, its CW columns)
-      if (y_es) {
-        const int cpr = CW * y_es / 16;
-        uint8_t* gy = reinterpret_cast<uint8_t*>(p.out);
-        for (int id = lane; id < 32 * cpr; id += 32) {
-          const int rr = id / cpr, j = id - rr * cpr;
-          const int gm = m0 + quarter * 32 + rr;
-          if (gm < p.M)
-            *reinterpret_cast<int4*>(gy + ((size_t)gm * p.Cout + c0) * y_es + j * 16) =
-                *reinterpret_cast<const int4*>(slice + rr * slice_pitch + j * 16);
+      const int rows_ok = p.M - (m0 + quarter * 32);
+      if constexpr (Y_ES != 0) {
+        constexpr int CPR = CW * Y_ES / 16;
+        uint8_t* gy = reinterpret_cast<uint8_t*>(p.out) + ((size_t)(m0 + quarter * 32) * p.Cout + c0) * Y_ES;
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+          const int id = lane + i * 32;
+          const int rr = id / CPR, j = id % CPR;
+          if (rr < rows_ok)
+            *reinterpret_cast<int4*>(gy + (size_t)rr * p.Cout * Y_ES + j * 16) = *reinterpret_cast<const int4*>(slice + rr * PITCH + j * 16);
         }
       }
-      if (low_bits) {
-        uint8_t* gl = reinterpret_cast<uint8_t*>(is_res ? p.out_low : p.out);
-        if (low_bits == 8) {
-          constexpr int cpr = CW / 16;
-          for (int id = lane; id < 32 * cpr; id += 32) {
-            const int rr = id / cpr, j = id - rr * cpr;
-            const int gm = m0 + quarter * 32 + rr;
-            if (gm < p.M)
-              *reinterpret_cast<int4*>(gl + (size_t)gm * p.Cout + c0 + j * 16) =
-                  *reinterpret_cast<const int4*>(lowslice + rr * S::LOW_PITCH + j * 16);
-          }
-        } else {   // 4-bit: 32 channels -> 16 packed bytes
-          constexpr int cpr = CW / 32;
-          for (int id = lane; id < 32 * cpr; id += 32) {
-            const int rr = id / cpr, j = id - rr * cpr;
-            const int gm = m0 + quarter * 32 + rr;
-            if (gm < p.M) {
-              const uint4 a = *reinterpret_cast<const uint4*>(lowslice + rr * S::LOW_PITCH + j * 32);
-              const uint4 b = *reinterpret_cast<const uint4*>(lowslice + rr * S::LOW_PITCH + j * 32 + 16);
-              uint4 o;
-              o.x = pack_nibbles8(a.x, a.y); o.y = pack_nibbles8(a.z, a.w);
-              o.z = pack_nibbles8(b.x, b.y); o.w = pack_nibbles8(b.z, b.w);
-              *reinterpret_cast<uint4*>(gl + (((size_t)gm * p.Cout + c0 + j * 32) >> 1)) = o;
-            }
+      if (low_bits == 8) {
+        constexpr int CPR = CW / 16;
+        uint8_t* gl = reinterpret_cast<uint8_t*>(IS_RES ? p.out_low : p.out) + (size_t)(m0 + quarter * 32) * p.Cout + c0;
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+          const int id = lane + i * 32;
+          const int rr = id / CPR, j = id % CPR;
+          if (rr < rows_ok)
+            *reinterpret_cast<int4*>(gl + (size_t)rr * p.Cout + j * 16) = *reinterpret_cast<const int4*>(lowslice + rr * S::LOW_PITCH + j * 16);
+        }
+      } else if (low_bits == 4) {   // 32 channels -> 16 packed bytes
+        constexpr int CPR = CW / 32;
+        uint8_t* gl = reinterpret_cast<uint8_t*>(IS_RES ? p.out_low : p.out) + (((size_t)(m0 + quarter * 32) * p.Cout + c0) >> 1);
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+          const int id = lane + i * 32;
+          const int rr = id / CPR, j = id % CPR;
+          if (rr < rows_ok) {
+            const uint4 a = *reinterpret_cast<const uint4*>(lowslice + rr * S::LOW_PITCH + j * 32);
+            const uint4 b = *reinterpret_cast<const uint4*>(lowslice + rr * S::LOW_PITCH + j * 32 + 16);
+            uint4 o;
+            o.x = pack_nibbles8(a.x, a.y); o.y = pack_nibbles8(a.z, a.w);
+            o.z = pack_nibbles8(b.x, b.y); o.w = pack_nibbles8(b.z, b.w);
+            *reinterpret_cast<uint4*>(gl + (((size_t)rr * p.Cout) >> 1) + j * 16) = o;
           }
         }
       }
       __syncwarp();   // slices are reused by the next tile
     }
-    if (is_res && p.y_bits == 16 && ymax > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
+    if constexpr (IS_RES) {
+      cp_async_wait<0>();
+      if (Y_ES == 2 && ymax > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
+    }
     if (bad) atomicOr(p.status, HAWQ_FLAG_BAD_RATIO);
   }
 
