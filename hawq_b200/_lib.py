@@ -41,7 +41,9 @@ class hawq_epilogue_desc(C.Structure):
 EPI_REQUANT, EPI_RESIDUAL, EPI_RAW_I32, EPI_DEQUANT_F32 = 0, 1, 2, 3
 FLAG_RESIDUAL_OVERFLOW = 1
 FLAG_BAD_RATIO = 2
+FLAG_REQUANT_OVERFLOW = 4
 EP_RATIOS_LE_ONE = 1
+EP_RATIOS_LE_2P20 = 2
 
 _vp, _i32, _i64, _u32, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float
 _conv_args = [_vp, C.POINTER(hawq_conv_desc), C.POINTER(hawq_epilogue_desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]

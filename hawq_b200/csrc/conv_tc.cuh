@@ -146,7 +146,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n, bool a_signed
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <int BN, int EPI>
+// WIDE: dyadic ratios up to 2^20 are allowed (e >= 11).  The FMA result is then checked to be a valid int32
+// (high word + sign bit of the low word must equal the high word of 1.5 * 2^52); a violation raises
+// HAWQ_FLAG_REQUANT_OVERFLOW so the host can re-run on the saturating generic kernels.
+template <int BN, int EPI, bool WIDE>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams p) {
   using S = TcSmem<BN, EPI>;
   constexpr int BM = TC_BM, STAGES = TC_STAGES;
@@ -281,8 +284,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     const int q_hi = (EPI == TC_EPI_REQ) ? p.hi : p.low_hi;
     constexpr double kMagic = 6755399441055744.0, kOffS = 4503601774854144.0, kOffU = 4503599627370496.0;
     constexpr int RES_CPR = CW * RES_ES / 16;    // 16-byte chunks per residual row
-    int ymax = 0, bad = 0;
+    int ymax = 0, bad = 0, ovf = 0;
     int cur_n0 = -1;
+    auto ratio_ok = [](uint32_t m, int e) { return m == 0u || e >= (WIDE ? 11 : 31); };
     uint32_t tile_iter = 0;
 
     auto prefetch_residual = [&](int tile, uint8_t* dst) {
@@ -316,14 +320,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         for (int i = tid - (TC_MMA_WARP + 1) * 32; i < BN; i += TC_EPI_WARPS * 32) {
           const hawq_chan ch = p.chan[n0 + i];
           sCst[i] = make_double2(kOffS - (double)ch.bias, dyadic_to_double(ch.m, ch.e));
-          bad |= !dyadic_is_fast(ch.m, ch.e);
+          bad |= !ratio_ok(ch.m, ch.e);
           if constexpr (IS_RES) {
             if (p.res_kind == 1) {
               const hawq_chan rc = p.res_chan[n0 + i];
               sM1[i] = dyadic_to_double(rc.m, rc.e);
-              bad |= !dyadic_is_fast(rc.m, rc.e);
+              bad |= !ratio_ok(rc.m, rc.e);
             } else {
               sM1[i] = dyadic_to_double(p.res_m, p.res_e);
+              bad |= !ratio_ok(p.res_m, p.res_e);
             }
           }
         }
@@ -406,10 +411,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
               for (int k = 0; k < 8; ++k) {
                 const double2 cm = cst[jj + k];
                 const double d = __hiloint2double(0x43300000, acc[jj + k] ^ 0x80000000) - cm.x;
-                const int v = __double2loint(__fma_rn(d, cm.y, kMagic));
+                const double qv = __fma_rn(d, cm.y, kMagic);
+                const int v = __double2loint(qv);
                 const double dr = (RES_ES == 2) ? (__hiloint2double(0x43300000, r[k]) - kOffU)
                                                 : (__hiloint2double(0x43300000, r[k] ^ 0x80000000) - kOffS);
-                y[k] = max(sat_add(__double2loint(__fma_rn(dr, m1[jj + k], kMagic)), v), relu_floor);
+                const double qr = __fma_rn(dr, m1[jj + k], kMagic);
+                const int vr = __double2loint(qr);
+                if constexpr (WIDE) {
+                  ovf |= (__double2hiint(qv) + (int)((uint32_t)v >> 31)) ^ 0x43380000;
+                  ovf |= (__double2hiint(qr) + (int)((uint32_t)vr >> 31)) ^ 0x43380000;
+                }
+                y[k] = max(sat_add(vr, v), relu_floor);
               }
               if (low_bits) {
 #pragma unroll
@@ -493,6 +505,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       if (Y_ES == 2 && ymax > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
     }
     if (bad) atomicOr(p.status, HAWQ_FLAG_BAD_RATIO);
+    if (ovf) atomicOr(p.status, HAWQ_FLAG_REQUANT_OVERFLOW);
   }
 
   // ---- teardown ----

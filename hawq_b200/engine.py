@@ -51,36 +51,39 @@ class CompiledModel:
         qtensor.config.residual_bits = 32
         return out
 
-    def _build(self, bits):
+    def _build(self, bits, key=None):
+        key = bits if key is None else key
         idx = self.device.index
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             before = ops.launch_count
             out = self._forward(bits)                  # warm-up: builds all parameter caches
-            self.launches[bits] = ops.launch_count - before
+            self.launches[key] = ops.launch_count - before
             self._forward(bits)
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
+        self.bits_of = getattr(self, 'bits_of', {})
+        self.bits_of[key] = bits
         if not self.use_graph:
-            self.outs[bits] = out
+            self.outs[key] = out
             return
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             ops.reset_status(idx)
             out = self._forward(bits)
             ops.copy_status(idx, self.flag)
-        self.graphs[bits] = g
-        self.outs[bits] = out
+        self.graphs[key] = g
+        self.outs[key] = out
 
-    def _run(self, bits):
+    def _run(self, key):
         if self.use_graph:
-            self.graphs[bits].replay()
+            self.graphs[key].replay()
         else:
             ops.reset_status(self.device.index)
-            self.outs[bits] = self._forward(bits)
+            self.outs[key] = self._forward(self.bits_of[key])
             ops.copy_status(self.device.index, self.flag)
-        return self.outs[bits]
+        return self.outs[key]
 
     def run_async(self, x=None):
         """Enqueue one forward (no host sync, no overflow check); returns the static logits tensor."""
@@ -94,13 +97,23 @@ class CompiledModel:
         flags = int(self.flag.item())
         if flags & 2:
             raise RuntimeError("hawq_b200: HAWQ_FLAG_BAD_RATIO raised (a dyadic ratio > 1 reached the fast kernel): results invalid")
-        if self.residual_bits == 16:
-            if flags & 1:
-                self.fallbacks += 1
-                if 32 not in self.outs:
-                    with torch.no_grad():
-                        self._build(32)
-                out = self._run(32)
+        if flags & 4:                          # a ratio > 1 term left int32 on the fast path: saturating generic kernels
+            self.fallbacks += 1
+            ops.fast_kernels = False
+            try:
+                with torch.no_grad():
+                    if "safe" not in self.outs:
+                        self._build(32, key="safe")
+                    out = self._run("safe")
+            finally:
+                ops.fast_kernels = True
+            return out
+        if self.residual_bits == 16 and flags & 1:
+            self.fallbacks += 1
+            if 32 not in self.outs:
+                with torch.no_grad():
+                    self._build(32)
+            out = self._run(32)
         return out
 
     @property

@@ -101,15 +101,26 @@ def epilogue(mode, relu=0, out_bits=0, clamp=(0, 0), res_kind=0, res_bits=0, res
                               y_bits, low_bits, low_me[0], low_me[1], low_clamp[0], low_clamp[1], cout_store, flags)
 
 
-def ratios_le_one(*pairs):
-    """True when every (m, e) pair (or (m list, e list)) has ratio m * 2^-e <= 1: the HAWQ_EP_RATIOS_LE_ONE promise."""
+fast_kernels = True   # set False to withhold the HAWQ_EP_* promises (always-saturating generic kernels)
+
+
+def ratio_flags(*pairs):
+    """HAWQ_EP_RATIOS_* promise for a set of (m, e) pairs (or (m list, e list)): LE_ONE when every ratio m * 2^-e <= 1
+    (e >= 31 or m == 0), LE_2P20 when every ratio <= 2^20 (e >= 11), else 0."""
+    if not fast_kernels:
+        return 0
+    min_e = 99
     for m, e in pairs:
         ms = m if isinstance(m, (list, tuple)) else [m]
         es = e if isinstance(e, (list, tuple)) else [e]
         for mi, ei in zip(ms, es):
-            if not (mi == 0 or ei >= 31):
-                return False
-    return True
+            if mi != 0:
+                min_e = min(min_e, ei)
+    if min_e >= 31:
+        return _lib.EP_RATIOS_LE_ONE
+    if min_e >= 11:
+        return _lib.EP_RATIOS_LE_2P20
+    return 0
 
 
 def conv2d(x, desc, ep, w, chan, res=None, res_chan=None, fscale=None, out=None, out_low=None):

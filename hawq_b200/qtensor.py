@@ -311,7 +311,7 @@ def _conv_case0(n, act, device):
     lo, hi = _act_clamp(act)
     out = _alloc(device, nb * ho * wo * ent["cout"], bits)
     ep = ops.epilogue(EPI_REQUANT, relu=n.relu, out_bits=bits, clamp=(lo, hi),
-                      flags=EP_RATIOS_LE_ONE if ops.ratios_le_one((m, e)) else 0)
+                      flags=ops.ratio_flags((m, e)))
     _launch_conv(n, ent, ep, chan, device, out=out)
     return Node("int", (nb, ent["cout"], ho, wo), data=out, bits=bits, signed=(act.quant_mode == "symmetric"))
 
@@ -323,7 +323,7 @@ def _conv_raw(n, device):
     chan = _chan_tensor(ent, "raw", [0] * ent["cout"], [1] * ent["cout"], device)
     nb, _, _, ho, wo = _conv_out_hw(n, ent)
     out = _alloc(device, nb * ho * wo * ent["cout"], 32)
-    _launch_conv(n, ent, ops.epilogue(EPI_RAW_I32, flags=EP_RATIOS_LE_ONE), chan, device, out=out)
+    _launch_conv(n, ent, ops.epilogue(EPI_RAW_I32, flags=ops.ratio_flags()), chan, device, out=out)
     return out, ent
 
 
@@ -368,7 +368,7 @@ def _launch_residual(r, low_act, device):
         low_node = Node("int", (nb, ent["cout"], ho, wo), data=low, bits=low_act.activation_bit,
                         signed=(low_act.quant_mode == "symmetric"))
     ep = ops.epilogue(EPI_RESIDUAL, relu=r.relu, res_kind=res_kind, res_bits=res_bits, res_me=res_me, y_bits=y_bits,
-                      flags=EP_RATIOS_LE_ONE if ops.ratios_le_one(*pairs) else 0, **kw)
+                      flags=ops.ratio_flags(*pairs), **kw)
     _launch_conv(conv, ent, ep, chan, device, out=y, out_low=low, res=res, res_chan=res_chan)
     r.shape = (nb, ent["cout"], ho, wo)
     r.become_int(y, y_bits, signed=(y_bits == 32))

@@ -47,7 +47,8 @@ enum hawq_status {
 
 /* bits of the device status word */
 #define HAWQ_FLAG_RESIDUAL_OVERFLOW 1   /* a post-ReLU residual value exceeded 65535 while stored as uint16 */
-#define HAWQ_FLAG_BAD_RATIO 2           /* HAWQ_EP_RATIOS_LE_ONE was promised but a ratio > 1 was found: results invalid */
+#define HAWQ_FLAG_BAD_RATIO 2           /* a HAWQ_EP_RATIOS_* promise was broken: results invalid */
+#define HAWQ_FLAG_REQUANT_OVERFLOW 4     /* a requantised value left int32 on the fast path (ratio > 1): re-run without HAWQ_EP_* flags */
 
 /* Per-output-channel epilogue parameters (16 B, one vector load per channel).
  * bias = bias_integer (quant_modules.py:481-484), (m, e) = batch_frexp of the requant ratio of that channel. */
@@ -99,6 +100,9 @@ typedef struct {
  * e >= 31 or m == 0 (true for every HAWQ ResNet layer).  Enables the tcgen05 kernel, which evaluates RHE(v * m / 2^e) with one
  * exact FP64 FMA.  The kernel re-checks the promise and raises HAWQ_FLAG_BAD_RATIO instead of computing wrong numbers. */
 #define HAWQ_EP_RATIOS_LE_ONE 1
+/* Weaker promise: every ratio <= 2^20 (e >= 11 or m == 0).  Same fast kernel plus an exact per-value check that the
+ * requantised term fits int32; a violation raises HAWQ_FLAG_REQUANT_OVERFLOW (the generic kernels saturate instead). */
+#define HAWQ_EP_RATIOS_LE_2P20 2
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------- */
 int hawq_abi_version(void);

@@ -143,6 +143,39 @@ def test_conv_residual(geom, a_bits, tc):
             assert torch.equal(a, b), (geom, a_bits, res_kind, res_bits, y_bits, low_bits, k_, tc)
 
 
+@pytest.mark.parametrize("geom", [CONV_GEOMS[0], CONV_GEOMS[3], CONV_GEOMS[5]])
+def test_conv_residual_wide_ratios_on_tensor_cores(geom):
+    """HAWQ_EP_RATIOS_LE_2P20: ratios above 1 (typical for the 16-bit residual requant) stay on the tcgen05 kernel."""
+    n, h, w, cin, cout, k, s, p = geom
+    r = rng(4242 + sum(geom))
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    numel = n * ho * wo * cout
+    x = rand_act(r, n * h * w * cin, 8)
+    wt = torch.from_numpy(r.randint(-8, 8, size=(cout, k, k, cin)).astype(np.int8))
+    chan = make_chan(r, cout, bias_mag=2000, ratio_lo=0.2, ratio_hi=40.0)
+    d = ops.conv_desc(n, h, w, cin, cout, k, k, s, p, 8)
+    for res_kind, res_bits, y_bits, low_bits in [(0, 16, 16, 8), (0, 32, 32, 4), (1, 32, 16, 8)]:
+        res = rand_act(r, numel, res_bits if res_kind == 0 else 32)
+        if res_bits == 16 and res_kind == 0:
+            res = torch.from_numpy(r.randint(0, 900, size=numel).astype(np.uint16).view(np.int16))
+        res_chan = make_chan(r, cout, ratio_lo=0.5, ratio_hi=3.0) if res_kind == 1 else None
+        ep = ops.epilogue(EPI_RESIDUAL, relu=1, res_kind=res_kind, res_bits=res_bits, res_me=dyadic(1.37), y_bits=y_bits,
+                          low_bits=low_bits, low_me=dyadic(0.0004), low_clamp=(0, 15) if low_bits == 4 else (-128, 127), flags=2)
+        ops.reset_status(0)
+        cs, gs = run_both("conv2d", dict(x=x, desc=d, ep=ep, w=wt, chan=chan, res=res, res_chan=res_chan, out=out_buf(numel, y_bits),
+                                         out_low=out_buf(numel, low_bits)), ["out", "out_low"])
+        assert ops.get_status(0) & 6 == 0
+        for a, b in zip(cs, gs):
+            assert torch.equal(a, b), (geom, res_kind, res_bits, y_bits, low_bits)
+    # a term that leaves int32 on the fast path must raise HAWQ_FLAG_REQUANT_OVERFLOW (the generic kernel would saturate)
+    res = torch.full((numel,), 2 ** 30, dtype=torch.int32)
+    ep = ops.epilogue(EPI_RESIDUAL, relu=1, res_kind=0, res_bits=32, res_me=dyadic(1000.0), y_bits=32, flags=2)
+    ops.reset_status(0)
+    ops.conv2d(x.to(DEV), d, ep, wt.to(DEV), chan.to(DEV), res=res.to(DEV), out=torch.zeros(numel, dtype=torch.int32, device=DEV))
+    assert ops.get_status(0) & 4
+    ops.reset_status(0)
+
+
 def test_residual_overflow_flag():
     r = rng(5)
     n, h, w, cin, cout = 1, 4, 4, 64, 64
