@@ -67,8 +67,10 @@ static int set_conv_attr() {
 
 template <int EPI, bool WIDE>
 static int set_tc_attr1() {
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI>::TOTAL));
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64, EPI, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, EPI>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, WIDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI, false>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64, EPI, WIDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, EPI, false>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI, true>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64, EPI, WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, EPI, true>::TOTAL));
   return HAWQ_OK;
 }
 template <int EPI>
@@ -78,17 +80,22 @@ static int set_tc_attr() {
   return rc;
 }
 
+template <int EPI, bool WIDE, bool A4>
+static void launch_tc2(const ConvParams& p, bool bn128, int grid, cudaStream_t st) {
+  if (bn128) conv_tc_kernel<128, EPI, WIDE, A4><<<grid, TC_THREADS, TcSmem<128, EPI, A4>::TOTAL, st>>>(p);
+  else conv_tc_kernel<64, EPI, WIDE, A4><<<grid, TC_THREADS, TcSmem<64, EPI, A4>::TOTAL, st>>>(p);
+}
 template <int EPI>
-static void launch_tc(const ConvParams& p, bool bn128, bool ratios_wide, int grid, cudaStream_t st) {
+static void launch_tc(const ConvParams& p, bool bn128, bool ratios_wide, bool a4, int grid, cudaStream_t st) {
   if constexpr (EPI >= TC_EPI_RES22) {
     if (ratios_wide) {
-      if (bn128) conv_tc_kernel<128, EPI, true><<<grid, TC_THREADS, TcSmem<128, EPI>::TOTAL, st>>>(p);
-      else conv_tc_kernel<64, EPI, true><<<grid, TC_THREADS, TcSmem<64, EPI>::TOTAL, st>>>(p);
+      if (a4) launch_tc2<EPI, true, true>(p, bn128, grid, st);
+      else launch_tc2<EPI, true, false>(p, bn128, grid, st);
       return;
     }
   }
-  if (bn128) conv_tc_kernel<128, EPI, false><<<grid, TC_THREADS, TcSmem<128, EPI>::TOTAL, st>>>(p);
-  else conv_tc_kernel<64, EPI, false><<<grid, TC_THREADS, TcSmem<64, EPI>::TOTAL, st>>>(p);
+  if (a4) launch_tc2<EPI, false, true>(p, bn128, grid, st);
+  else launch_tc2<EPI, false, false>(p, bn128, grid, st);
 }
 
 template <int BN, bool A4>
@@ -237,18 +244,19 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
                       ep->mode == HAWQ_EPI_RAW_I32;
   const bool ratios_one = (ep->flags & HAWQ_EP_RATIOS_LE_ONE) != 0;
   const bool ratios_wide = !ratios_one && (ep->flags & HAWQ_EP_RATIOS_LE_2P20) != 0 && ep->mode == HAWQ_EPI_RESIDUAL;
-  if (tc_enabled && d->a_bits == 8 && tc_epi && (ratios_one || ratios_wide)) {
+  if (tc_enabled && tc_epi && (ratios_one || ratios_wide)) {
+    const bool a4 = d->a_bits == 4;
     const bool wide = (d->Cout % 128 == 0);
     const long long tiles = ((M + TC_BM - 1) / TC_BM) * (d->Cout / (wide ? 128 : 64));
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
     cudaStream_t st = (cudaStream_t)stream;
-    if (ep->mode == HAWQ_EPI_REQUANT) launch_tc<TC_EPI_REQ>(p, wide, false, grid, st);
-    else if (ep->mode == HAWQ_EPI_RAW_I32) launch_tc<TC_EPI_RAW>(p, wide, false, grid, st);
+    if (ep->mode == HAWQ_EPI_REQUANT) launch_tc<TC_EPI_REQ>(p, wide, false, a4, grid, st);
+    else if (ep->mode == HAWQ_EPI_RAW_I32) launch_tc<TC_EPI_RAW>(p, wide, false, a4, grid, st);
     else {
       const int res_es = (ep->res_kind == 1 || ep->res_bits == 32) ? 4 : 2;
-      if (res_es == 2 && ep->y_bits == 16) launch_tc<TC_EPI_RES22>(p, wide, ratios_wide, grid, st);
-      else if (res_es == 4 && ep->y_bits == 32) launch_tc<TC_EPI_RES44>(p, wide, ratios_wide, grid, st);
-      else if (res_es == 4 && ep->y_bits == 16) launch_tc<TC_EPI_RES42>(p, wide, ratios_wide, grid, st);
+      if (res_es == 2 && ep->y_bits == 16) launch_tc<TC_EPI_RES22>(p, wide, ratios_wide, a4, grid, st);
+      else if (res_es == 4 && ep->y_bits == 32) launch_tc<TC_EPI_RES44>(p, wide, ratios_wide, a4, grid, st);
+      else if (res_es == 4 && ep->y_bits == 16) launch_tc<TC_EPI_RES42>(p, wide, ratios_wide, a4, grid, st);
       else goto legacy;   // uint16 residual in, int32 out: not a combination the engine produces
     }
     return launch_check("conv_tc");

@@ -37,7 +37,7 @@ constexpr int TC_EPI_RES22 = 2;    // RESIDUAL: uint16 stream in, uint16 stream 
 constexpr int TC_EPI_RES44 = 3;    // RESIDUAL: int32 in (stream or identity-conv accumulator), int32 out
 constexpr int TC_EPI_RES42 = 4;    // RESIDUAL: int32 in, uint16 out
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool A4 = false>
 struct TcSmem {
   static constexpr int A_STAGE = TC_BM * 64;
   static constexpr int B_STAGE = BN * 64;
@@ -56,7 +56,9 @@ struct TcSmem {
   static constexpr int LOW_OFF = SLICES_OFF + TC_EPI_WARPS * SLICE * SLICE_BUFS;
   static constexpr int CST_OFF = LOW_OFF + TC_EPI_WARPS * LOW_SLICE;       // double2 {Cb, M}[BN]
   static constexpr int M1_OFF = CST_OFF + BN * 16;                         // double M1[BN]
-  static constexpr int BAR_OFF = M1_OFF + BN * 8;                          // mbarriers + tmem base
+  static constexpr int STG_SLOT = TC_BM * 32;                              // packed 4-bit rows of one k-tile (A4 only)
+  static constexpr int STG_OFF = M1_OFF + BN * 8;
+  static constexpr int BAR_OFF = STG_OFF + (A4 ? (TC_LAG + 1) * STG_SLOT : 0);   // mbarriers + tmem base
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;                       // + slack for 1024 B alignment of the ring
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
@@ -149,9 +151,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n, bool a_signed
 // WIDE: dyadic ratios up to 2^20 are allowed (e >= 11).  The FMA result is then checked to be a valid int32
 // (high word + sign bit of the low word must equal the high word of 1.5 * 2^52); a violation raises
 // HAWQ_FLAG_REQUANT_OVERFLOW so the host can re-run on the saturating generic kernels.
-template <int BN, int EPI, bool WIDE>
+// A4: activations are packed unsigned nibbles (hawq order).  They are fetched packed (half the bytes), parked in a small
+// staging ring and expanded to int8 by the producer thread that owns the row, directly into the swizzled A tile in the
+// K order the (host-permuted) weights expect: per 32-channel block {c0-3, c8-11, c16-19, c24-27 | c4-7, c12-15, ...}.
+template <int BN, int EPI, bool WIDE, bool A4>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams p) {
-  using S = TcSmem<BN, EPI>;
+  using S = TcSmem<BN, EPI, A4>;
   constexpr int BM = TC_BM, STAGES = TC_STAGES;
   constexpr int CW = S::CW;                      // columns handled by one epilogue warp: 32 or 64
   constexpr int TMEM_COLS = 2 * BN;              // two accumulator buffers (power of two >= 32: 128 / 256)
@@ -200,6 +205,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     const uint32_t a_sw = (row >> 1) & 3;
     uint32_t it = 0;                           // global k-tile counter (ring position)
     uint32_t pending = 0;                      // k-tiles issued but not yet signalled
+    // A4: expand this thread's packed row of k-tile j (64 nibbles) into the int8 A tile of that k-tile's stage
+    auto expand_row = [&](uint32_t j) {
+      const uint8_t* stg = smem + S::STG_OFF + (j % (TC_LAG + 1)) * S::STG_SLOT + row * 32;
+      uint8_t* dst = smem + (j % STAGES) * S::STAGE + a_off;
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {      // 32 channels = 16 packed bytes -> 32 int8 = chunks 2*blk, 2*blk+1
+        const uint4 w = *reinterpret_cast<const uint4*>(stg + blk * 16);
+        const uint4 lo = make_uint4(w.x & 0x0F0F0F0Fu, w.y & 0x0F0F0F0Fu, w.z & 0x0F0F0F0Fu, w.w & 0x0F0F0F0Fu);
+        const uint4 hi = make_uint4((w.x >> 4) & 0x0F0F0F0Fu, (w.y >> 4) & 0x0F0F0F0Fu, (w.z >> 4) & 0x0F0F0F0Fu, (w.w >> 4) & 0x0F0F0F0Fu);
+        *reinterpret_cast<uint4*>(dst + (((2 * blk) ^ a_sw) << 4)) = lo;
+        *reinterpret_cast<uint4*>(dst + (((2 * blk + 1) ^ a_sw) << 4)) = hi;
+      }
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       const int m = m0 + row;
@@ -219,10 +237,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         {
           const int hi = hi0 + kh, wi = wi0 + kw;
           const bool v = a_ok && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W;
-          const uint8_t* src = v ? p.x + (size_t)(pix + hi * p.W + wi) * p.x_pix_bytes + c * 64 : p.x;
           const int nb = v ? 16 : 0;
+          if constexpr (!A4) {
+            const uint8_t* src = v ? p.x + (size_t)(pix + hi * p.W + wi) * p.x_pix_bytes + c * 64 : p.x;
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) cp_async_16(a_base + a_off + ((ch ^ a_sw) << 4), src + ch * 16, nb);
+            for (int ch = 0; ch < 4; ++ch) cp_async_16(a_base + a_off + ((ch ^ a_sw) << 4), src + ch * 16, nb);
+          } else {
+            const uint8_t* src = v ? p.x + (size_t)(pix + hi * p.W + wi) * p.x_pix_bytes + c * 32 : p.x;
+            const uint32_t stg = smem_base + S::STG_OFF + (it % (TC_LAG + 1)) * S::STG_SLOT + row * 32;
+            cp_async_16(stg, src, nb);
+            cp_async_16(stg + 16, src + 16, nb);
+          }
         }
 #pragma unroll
         for (int i = 0; i < BN / 32; ++i) {     // B: BN rows x 4 chunks over 128 threads
@@ -234,6 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         ++pending;
         if (pending > TC_LAG) {                 // the group issued LAG iterations ago has landed
           cp_async_wait<TC_LAG>();
+          if constexpr (A4) expand_row(it - TC_LAG);
           fence_proxy_async();
           mbar_arrive(full_bar((it - TC_LAG) % STAGES));
           --pending;
@@ -243,12 +269,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     }
     // drain
     cp_async_wait<0>();
+    if constexpr (A4)
+      for (uint32_t j = pending; j > 0; --j) expand_row(it - j);
     fence_proxy_async();
     for (uint32_t j = pending; j > 0; --j) mbar_arrive(full_bar((it - j) % STAGES));
   } else if (warp == TC_MMA_WARP) {
     // =============================================================================== MMA issuer (one lane)
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_i8(BM, BN, true);
+      const uint32_t idesc = umma_idesc_i8(BM, BN, !A4);   // packed 4-bit activations are unsigned
       uint32_t it = 0, tile_iter = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
         const int buf = tile_iter & 1;
