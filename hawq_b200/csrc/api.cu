@@ -21,6 +21,7 @@ struct hawq_handle {
 };
 
 static thread_local char g_err[512] = "";
+static long long* g_trace = nullptr;   // hawq_debug_set_trace
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -195,6 +196,7 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   p.y_bits = ep->y_bits; p.low_bits = ep->low_bits; p.low_m = ep->low_m; p.low_e = ep->low_e;
   p.low_lo = ep->low_lo; p.low_hi = ep->low_hi; p.cout_store = ep->cout_store;
   p.slow_scalar = 0;
+  p.trace = g_trace;
   if (ep->mode == HAWQ_EPI_RESIDUAL) {
     if (ep->res_kind == 0 && !dyadic_is_fast(ep->res_m, ep->res_e)) p.slow_scalar = 1;
     if (ep->low_bits != 0 && !dyadic_is_fast(ep->low_m, ep->low_e)) p.slow_scalar = 1;
@@ -436,5 +438,10 @@ int hawq_permute_weights_for_i4(int8_t* host_w, int64_t rows_times_taps, int32_t
 }
 
 int64_t hawq_workspace_bytes(const hawq_conv_desc*, const hawq_epilogue_desc*) { return 0; }
+
+int hawq_debug_set_trace(int64_t* device_buffer) {
+  g_trace = reinterpret_cast<long long*>(device_buffer);
+  return HAWQ_OK;
+}
 
 }  // extern "C"

@@ -40,6 +40,7 @@ struct ConvParams {
   int low_e, low_lo, low_hi;
   int cout_store;
   int slow_scalar;   // host-checked: a scalar dyadic pair (res / low) has ratio > 1 -> generic 64-bit requant
+  long long* trace;  // debug timeline (hawq_debug_set_trace): [role][tile][event] clock64 values of CTA 0, or null
 };
 
 constexpr int CONV_BM = 128;

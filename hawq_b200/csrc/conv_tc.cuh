@@ -176,6 +176,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::BAR_OFF + 8 * (2 * STAGES + 4));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // debug timeline: role 0 producer (warp 0), 1 MMA, 2 epilogue (first epilogue warp); 8 events x 64 tiles per role
+  auto trace = [&](int role, uint32_t tile_i, int ev) {
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tile_i < 64) p.trace[(role * 64 + tile_i) * 8 + ev] = clock64();
+  };
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.Cout / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int KT = p.KH * p.KW * p.cin_chunks;
@@ -229,9 +233,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       const int hi0 = ho * p.stride - p.pad, wi0 = wo * p.stride - p.pad, pix = n * p.H * p.W;
       const int8_t* wrow = p.w + (size_t)n0 * p.K;
       int c = 0, kw = 0, kh = 0;
+      const uint32_t ptile = (tile - blockIdx.x) / gridDim.x;
+      if (warp == 0) trace(0, ptile, 0);
       for (int kt = 0; kt < KT; ++kt, ++it) {
         const int stage = it % STAGES;
         mbar_wait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
+        if (warp == 0 && kt == 0) trace(0, ptile, 1);
         const uint32_t a_base = smem_base + stage * S::STAGE;
         const uint32_t b_base = a_base + S::A_STAGE;
         {
@@ -266,6 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         }
         if (++c == p.cin_chunks) { c = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
       }
+      if (warp == 0) trace(0, ptile, 2);
     }
     // drain
     cp_async_wait<0>();
@@ -280,20 +288,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       uint32_t it = 0, tile_iter = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
         const int buf = tile_iter & 1;
+        trace(1, tile_iter, 0);
         mbar_wait(tempty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
+        trace(1, tile_iter, 1);
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kt = 0; kt < KT; ++kt, ++it) {
           const int stage = it % STAGES;
           mbar_wait(full_bar(stage), (it / STAGES) & 1);
           tc_fence_after();
+          if (kt == 0) trace(1, tile_iter, 2);
           const uint32_t a_addr = smem_base + stage * S::STAGE;
           const uint32_t b_addr = a_addr + S::A_STAGE;
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             umma_i8(d_tmem, umma_desc_sw64(a_addr + k * 32), umma_desc_sw64(b_addr + k * 32), idesc, (kt | k) != 0);
           umma_commit(empty_bar(stage));                          // smem stage reusable once these MMAs retire
-          if (kt == KT - 1) umma_commit(tfull_bar(buf));          // accumulator complete
+          if (kt == KT - 1) { umma_commit(tfull_bar(buf)); trace(1, tile_iter, 3); }   // accumulator complete
         }
       }
     }
@@ -374,14 +385,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         }
       }
 
+      if (ew == 0) trace(2, tile_iter, 0);
       mbar_wait(tfull_bar(buf), (tile_iter >> 1) & 1);
       tc_fence_after();
+      if (ew == 0) trace(2, tile_iter, 1);
       if constexpr (IS_RES) {
         if constexpr (S::SLICE_BUFS == 2) cp_async_wait<1>();
         else cp_async_wait<0>();
         __syncwarp();
       }
       uint8_t* myrow = slice + lane * PITCH;
+      if (ew == 0) trace(2, tile_iter, 2);
 
 #pragma unroll
       for (int cb = 0; cb < CW; cb += 32) {
@@ -485,6 +499,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (ew == 0) trace(2, tile_iter, 3);
 
       // coalesced copy-out of the staged outputs (rows of this warp's lane quarter, its CW columns)
       const int rows_ok = p.M - (m0 + quarter * 32);
@@ -527,6 +542,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         }
       }
       __syncwarp();   // slices are reused by the next tile
+      if (ew == 0) trace(2, tile_iter, 4);
     }
     if constexpr (IS_RES) {
       cp_async_wait<0>();

@@ -187,6 +187,9 @@ int hawq_dyadic(double ratio, uint32_t* m, int32_t* e);
 int64_t hawq_rhe_requant_host(int32_t v, uint32_t m, int32_t e);
 /* K permutation inside each 32-channel block for layers whose input is packed 4-bit (in place, int8 OHWI, host memory) */
 int hawq_permute_weights_for_i4(int8_t* host_w, int64_t rows_times_taps, int32_t Cin);
+/* debug: device int64[3][64][8] receiving clock64 timelines (producer / MMA / epilogue roles of CTA 0, first 64 tiles) of
+ * subsequent tcgen05 convolution launches; null switches tracing off.  Not for production use. */
+int hawq_debug_set_trace(int64_t* device_buffer);
 /* workspace query kept for ABI completeness: this build needs no scratch beyond caller tensors */
 int64_t hawq_workspace_bytes(const hawq_conv_desc* d, const hawq_epilogue_desc* ep);
 
