@@ -242,7 +242,7 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
 
   // tcgen05 path: int8 activations, the three hot epilogues, all ratios <= 1 (promised), HAWQ_B200_TC != 0
   static const bool tc_enabled = [] { const char* e = getenv("HAWQ_B200_TC"); return !(e && e[0] == '0'); }();
-  const bool tc_epi = (ep->mode == HAWQ_EPI_REQUANT && ep->out_bits <= 8) || (ep->mode == HAWQ_EPI_RESIDUAL && ep->y_bits != 0) ||
+  const bool tc_epi = (ep->mode == HAWQ_EPI_REQUANT && ep->out_bits <= 8) || (ep->mode == HAWQ_EPI_RESIDUAL && ep->y_bits != 0 && ep->relu) ||
                       ep->mode == HAWQ_EPI_RAW_I32;
   const bool ratios_one = (ep->flags & HAWQ_EP_RATIOS_LE_ONE) != 0;
   const bool ratios_wide = !ratios_one && (ep->flags & HAWQ_EP_RATIOS_LE_2P20) != 0 && ep->mode == HAWQ_EPI_RESIDUAL;

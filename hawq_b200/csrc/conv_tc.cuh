@@ -23,8 +23,6 @@
 namespace hawq {
 
 constexpr int TC_BM = 128;
-constexpr int TC_STAGES = 6;
-constexpr int TC_LAG = 3;                 // producer signals k-tile (it - LAG) after issuing k-tile it
 constexpr int TC_PRODUCER_WARPS = 4;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_MMA_WARP = TC_PRODUCER_WARPS;
@@ -39,27 +37,31 @@ constexpr int TC_EPI_RES42 = 4;    // RESIDUAL: int32 in, uint16 out
 
 template <int BN, int EPI, bool A4 = false>
 struct TcSmem {
+  // pipeline depth: RESIDUAL epilogues are epilogue-bound and need shared memory for their tiles; the others are
+  // load-latency-bound and get a deep ring.  The producer keeps LAG + 1 k-tiles in flight per thread.
+  static constexpr int STAGES = (EPI == TC_EPI_RES22) ? (A4 && BN == 128 ? 4 : 5) : (EPI >= TC_EPI_RES44) ? 5 : (EPI == TC_EPI_RAW) ? 7 : (BN == 128 ? 10 : 12);
+  static constexpr int LAG = STAGES - 2;
   static constexpr int A_STAGE = TC_BM * 64;
   static constexpr int B_STAGE = BN * 64;
   static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int RING = TC_STAGES * STAGE;
+  static constexpr int RING = STAGES * STAGE;
   static constexpr int CW = BN / 2;                                        // columns per epilogue warp
   static constexpr int RES_ES = (EPI == TC_EPI_RES22) ? 2 : (EPI >= TC_EPI_RES44 ? 4 : 0);
   static constexpr int Y_ES = (EPI == TC_EPI_RES22 || EPI == TC_EPI_RES42) ? 2 : ((EPI == TC_EPI_RES44 || EPI == TC_EPI_RAW) ? 4 : 0);
   static constexpr int SLICE_ES = RES_ES > Y_ES ? RES_ES : Y_ES;
   static constexpr int SLICE_PITCH = CW * SLICE_ES + 16;                   // +16 B: 16-byte row-per-lane accesses conflict-free
   static constexpr int SLICE = SLICE_ES ? 32 * SLICE_PITCH : 0;
-  static constexpr int SLICE_BUFS = (EPI == TC_EPI_RES22) ? 2 : 1;         // uint16 residual tiles are prefetched one tile ahead
+  static constexpr int SLICE_BUFS = (EPI == TC_EPI_RES22) ? 3 : 1;         // RES22: 2 prefetch + 1 output; RES4x: in place; RAW: output
   static constexpr int LOW_PITCH = CW + 16;
-  static constexpr int LOW_SLICE = 32 * LOW_PITCH;
+  static constexpr int LOW_SLICE = (EPI == TC_EPI_RAW) ? 0 : 32 * LOW_PITCH;
   static constexpr int SLICES_OFF = RING;
   static constexpr int LOW_OFF = SLICES_OFF + TC_EPI_WARPS * SLICE * SLICE_BUFS;
   static constexpr int CST_OFF = LOW_OFF + TC_EPI_WARPS * LOW_SLICE;       // double2 {Cb, M}[BN]
   static constexpr int M1_OFF = CST_OFF + BN * 16;                         // double M1[BN]
   static constexpr int STG_SLOT = TC_BM * 32;                              // packed 4-bit rows of one k-tile (A4 only)
   static constexpr int STG_OFF = M1_OFF + BN * 8;
-  static constexpr int BAR_OFF = STG_OFF + (A4 ? (TC_LAG + 1) * STG_SLOT : 0);   // mbarriers + tmem base
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;                       // + slack for 1024 B alignment of the ring
+  static constexpr int BAR_OFF = STG_OFF + (A4 ? (LAG + 1) * STG_SLOT : 0);   // mbarriers + tmem base
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;                       // + slack for 1024 B alignment of the ring
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
@@ -137,6 +139,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// asynchronous row store smem -> global through the bulk-copy engine (bytes % 16 == 0, both 16-byte aligned)
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // UMMA shared-memory descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row atoms of 512 B (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
@@ -154,10 +164,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n, bool a_signed
 // A4: activations are packed unsigned nibbles (hawq order).  They are fetched packed (half the bytes), parked in a small
 // staging ring and expanded to int8 by the producer thread that owns the row, directly into the swizzled A tile in the
 // K order the (host-permuted) weights expect: per 32-channel block {c0-3, c8-11, c16-19, c24-27 | c4-7, c12-15, ...}.
+// Preconditions (promised via HAWQ_EP_RATIOS_*, re-checked -> HAWQ_FLAG_BAD_RATIO): ratios within the bound,
+// |bias| < 2^29 (sums of two requantised terms then cannot wrap), RESIDUAL launches have relu = 1.
 template <int BN, int EPI, bool WIDE, bool A4>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams p) {
   using S = TcSmem<BN, EPI, A4>;
-  constexpr int BM = TC_BM, STAGES = TC_STAGES;
+  constexpr int BM = TC_BM, STAGES = S::STAGES, LAG = S::LAG;
   constexpr int CW = S::CW;                      // columns handled by one epilogue warp: 32 or 64
   constexpr int TMEM_COLS = 2 * BN;              // two accumulator buffers (power of two >= 32: 128 / 256)
   constexpr int RES_ES = S::RES_ES, Y_ES = S::Y_ES, PITCH = S::SLICE_PITCH;
@@ -205,13 +217,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   if (warp < TC_PRODUCER_WARPS) {
     // =============================================================================== producers (128 threads)
     const int row = tid;                       // A row of the tile owned by this thread
-    const uint32_t a_off = swz<64>(row, 0) & ~63u;                 // row base; chunk c lives at a_off + ((c ^ sw) << 4)
+    const uint32_t a_off = row * 64;           // row base; chunk c lives at a_off + ((c ^ a_sw) << 4)  (SWIZZLE_64B)
     const uint32_t a_sw = (row >> 1) & 3;
     uint32_t it = 0;                           // global k-tile counter (ring position)
     uint32_t pending = 0;                      // k-tiles issued but not yet signalled
     // A4: expand this thread's packed row of k-tile j (64 nibbles) into the int8 A tile of that k-tile's stage
     auto expand_row = [&](uint32_t j) {
-      const uint8_t* stg = smem + S::STG_OFF + (j % (TC_LAG + 1)) * S::STG_SLOT + row * 32;
+      const uint8_t* stg = smem + S::STG_OFF + (j % (LAG + 1)) * S::STG_SLOT + row * 32;
       uint8_t* dst = smem + (j % STAGES) * S::STAGE + a_off;
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {      // 32 channels = 16 packed bytes -> 32 int8 = chunks 2*blk, 2*blk+1
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
             for (int ch = 0; ch < 4; ++ch) cp_async_16(a_base + a_off + ((ch ^ a_sw) << 4), src + ch * 16, nb);
           } else {
             const uint8_t* src = v ? p.x + (size_t)(pix + hi * p.W + wi) * p.x_pix_bytes + c * 32 : p.x;
-            const uint32_t stg = smem_base + S::STG_OFF + (it % (TC_LAG + 1)) * S::STG_SLOT + row * 32;
+            const uint32_t stg = smem_base + S::STG_OFF + (it % (LAG + 1)) * S::STG_SLOT + row * 32;
             cp_async_16(stg, src, nb);
             cp_async_16(stg + 16, src + 16, nb);
           }
@@ -264,11 +276,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         }
         cp_async_commit();
         ++pending;
-        if (pending > TC_LAG) {                 // the group issued LAG iterations ago has landed
-          cp_async_wait<TC_LAG>();
-          if constexpr (A4) expand_row(it - TC_LAG);
+        if (pending > LAG) {                    // the group issued LAG iterations ago has landed
+          cp_async_wait<LAG>();
+          if constexpr (A4) expand_row(it - LAG);
           fence_proxy_async();
-          mbar_arrive(full_bar((it - TC_LAG) % STAGES));
+          mbar_arrive(full_bar((it - LAG) % STAGES));
           --pending;
         }
         if (++c == p.cin_chunks) { c = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
@@ -313,20 +325,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     const int ew = warp - (TC_MMA_WARP + 1);     // 0..7
     const int quarter = warp & 3;                // TMEM lane quarter this warp may access
     const int half = ew >> 2;                    // column half
+    // slices: RES22 -> [0],[1] residual prefetch ring, [2] output; RES4x -> [0] residual in / output in place; RAW -> [0] output
     uint8_t* slice0 = smem + S::SLICES_OFF + ew * S::SLICE * S::SLICE_BUFS;
+    uint8_t* yslice = slice0 + (S::SLICE_BUFS - 1) * S::SLICE;
     uint8_t* lowslice = smem + S::LOW_OFF + ew * S::LOW_SLICE;
+    uint8_t* myy = yslice + lane * PITCH;
     uint8_t* mylow = lowslice + lane * S::LOW_PITCH;
     const int low_bits = IS_RES ? p.low_bits : (EPI == TC_EPI_REQ ? p.out_bits : 0);
+    const int low_row_bytes = low_bits == 8 ? CW : CW / 2;
     const double low_M = dyadic_to_double(p.low_m, p.low_e);
-    const int relu_floor = p.relu ? 0 : (int)0x80000000;
+    const double res_M = dyadic_to_double(p.res_m, p.res_e);
     const int q_lo = (EPI == TC_EPI_REQ) ? (p.relu ? max(p.lo, 0) : p.lo) : p.low_lo;
     const int q_hi = (EPI == TC_EPI_REQ) ? p.hi : p.low_hi;
     constexpr double kMagic = 6755399441055744.0, kOffS = 4503601774854144.0, kOffU = 4503599627370496.0;
     constexpr int RES_CPR = CW * RES_ES / 16;    // 16-byte chunks per residual row
-    int ymax = 0, bad = 0, ovf = 0;
+    int ymax = 0, ovf = 0;
+    int bad = (IS_RES && !p.relu) ? 1 : 0;
     int cur_n0 = -1;
-    auto ratio_ok = [](uint32_t m, int e) { return m == 0u || e >= (WIDE ? 11 : 31); };
     uint32_t tile_iter = 0;
+    auto ratio_ok = [](uint32_t m, int e) { return m == 0u || e >= (WIDE ? 11 : 31); };
+    if (IS_RES && p.res_kind == 0) bad |= !ratio_ok(p.res_m, p.res_e);
+    if (low_bits && IS_RES) bad |= !dyadic_is_fast(p.low_m, p.low_e);
 
     auto prefetch_residual = [&](int tile, uint8_t* dst) {
       if constexpr (IS_RES) {
@@ -343,15 +362,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       }
       cp_async_commit();
     };
+    // pack 4 clamped values into 4 bytes
+    auto pack4 = [](int a, int b, int c, int d) { return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410); };
 
-    if constexpr (S::SLICE_BUFS == 2) {
+    if constexpr (EPI == TC_EPI_RES22) {
       if ((int)blockIdx.x < num_tiles) prefetch_residual(blockIdx.x, slice0);
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       const int buf = tile_iter & 1;
       const int c0 = n0 + half * CW;             // first global channel of this warp
-      uint8_t* slice = slice0 + (S::SLICE_BUFS == 2 ? (tile_iter & 1) * S::SLICE : 0);
+      uint8_t* rslice = slice0 + (EPI == TC_EPI_RES22 ? (tile_iter & 1) * S::SLICE : 0);
 
       // per-channel constants of this tile's channel block (shared by the 8 epilogue warps)
       if (n0 != cur_n0) {
@@ -359,15 +380,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         for (int i = tid - (TC_MMA_WARP + 1) * 32; i < BN; i += TC_EPI_WARPS * 32) {
           const hawq_chan ch = p.chan[n0 + i];
           sCst[i] = make_double2(kOffS - (double)ch.bias, dyadic_to_double(ch.m, ch.e));
-          bad |= !ratio_ok(ch.m, ch.e);
-          if constexpr (IS_RES) {
+          bad |= !ratio_ok(ch.m, ch.e) | (ch.bias >= (1 << 29)) | (ch.bias <= -(1 << 29));
+          if constexpr (EPI >= TC_EPI_RES44) {
             if (p.res_kind == 1) {
               const hawq_chan rc = p.res_chan[n0 + i];
               sM1[i] = dyadic_to_double(rc.m, rc.e);
               bad |= !ratio_ok(rc.m, rc.e);
             } else {
-              sM1[i] = dyadic_to_double(p.res_m, p.res_e);
-              bad |= !ratio_ok(p.res_m, p.res_e);
+              sM1[i] = res_M;
             }
           }
         }
@@ -375,14 +395,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         cur_n0 = n0;
       }
 
-      if constexpr (IS_RES) {
-        if constexpr (S::SLICE_BUFS == 2) {        // this tile's residual was prefetched; start the next one
-          const int nxt = tile + gridDim.x;
-          if (nxt < num_tiles) prefetch_residual(nxt, slice0 + ((tile_iter + 1) & 1) * S::SLICE);
-          else cp_async_commit();
-        } else {
-          prefetch_residual(tile, slice);
-        }
+      if constexpr (EPI == TC_EPI_RES22) {         // this tile's residual was prefetched; start the next one
+        const int nxt = tile + gridDim.x;
+        if (nxt < num_tiles) prefetch_residual(nxt, slice0 + ((tile_iter + 1) & 1) * S::SLICE);
+        else cp_async_commit();
+      } else if constexpr (IS_RES) {        // in-place variant: the previous tile's row stores must have left the buffer
+        bulk_wait_read_all();
+        __syncwarp();
+        prefetch_residual(tile, rslice);
       }
 
       if (ew == 0) trace(2, tile_iter, 0);
@@ -390,11 +410,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       tc_fence_after();
       if (ew == 0) trace(2, tile_iter, 1);
       if constexpr (IS_RES) {
-        if constexpr (S::SLICE_BUFS == 2) cp_async_wait<1>();
+        if constexpr (EPI == TC_EPI_RES22) cp_async_wait<1>();
         else cp_async_wait<0>();
-        __syncwarp();
       }
-      uint8_t* myrow = slice + lane * PITCH;
+      bulk_wait_read_all();            // the bulk stores of the previous tile have finished reading yslice / lowslice
+      __syncwarp();
+      const uint8_t* myres = rslice + lane * PITCH;
       if (ew == 0) trace(2, tile_iter, 2);
 
 #pragma unroll
@@ -403,35 +424,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + half * CW + cb, acc);
         tmem_ld_wait();
         const double2* cst = sCst + half * CW + cb;
-        const double* m1 = sM1 + half * CW + cb;
         if constexpr (EPI == TC_EPI_REQ) {
 #pragma unroll
           for (int j = 0; j < 32; j += 16) {
-            uint32_t w[4];
+            int q[16];
 #pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              int q[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const double2 cm = cst[j + g4 * 4 + k];
-                const double d = __hiloint2double(0x43300000, acc[j + g4 * 4 + k] ^ 0x80000000) - cm.x;
-                q[k] = clampi(__double2loint(__fma_rn(d, cm.y, kMagic)), q_lo, q_hi);
-              }
-              w[g4] = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+            for (int k = 0; k < 16; ++k) {
+              const double2 cm = cst[j + k];
+              const double d = __hiloint2double(0x43300000, acc[j + k] ^ 0x80000000) - cm.x;
+              q[k] = clampi(__double2loint(__fma_rn(d, cm.y, kMagic)), q_lo, q_hi);
             }
-            *reinterpret_cast<uint4*>(mylow + cb + j) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (low_bits == 8) {
+              *reinterpret_cast<uint4*>(mylow + cb + j) =
+                  make_uint4(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7]), pack4(q[8], q[9], q[10], q[11]), pack4(q[12], q[13], q[14], q[15]));
+            } else {
+              *reinterpret_cast<uint2*>(mylow + ((cb + j) >> 1)) =
+                  make_uint2(pack_nibbles8(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7])),
+                             pack_nibbles8(pack4(q[8], q[9], q[10], q[11]), pack4(q[12], q[13], q[14], q[15])));
+            }
           }
         } else if constexpr (EPI == TC_EPI_RAW) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            int4 o;   // bias = kOffS - Cb (exact); the double subtraction keeps everything on the FP64 pipe
+            int4 o;   // bias = kOffS - Cb (exact); (acc + bias) + magic is exact, the low word is the int32 sum
             o.x = __double2loint((__hiloint2double(0x43300000, acc[j + 0] ^ 0x80000000) - cst[j + 0].x) + kMagic);
             o.y = __double2loint((__hiloint2double(0x43300000, acc[j + 1] ^ 0x80000000) - cst[j + 1].x) + kMagic);
             o.z = __double2loint((__hiloint2double(0x43300000, acc[j + 2] ^ 0x80000000) - cst[j + 2].x) + kMagic);
             o.w = __double2loint((__hiloint2double(0x43300000, acc[j + 3] ^ 0x80000000) - cst[j + 3].x) + kMagic);
-            *reinterpret_cast<int4*>(myrow + (cb + j) * 4) = o;
+            *reinterpret_cast<int4*>(myy + (cb + j) * 4) = o;
           }
-        } else {   // RESIDUAL: groups of 8 channels (one 16-byte vector of uint16 residuals / two of int32)
+        } else {   // RESIDUAL (relu = 1): groups of 8 channels (one 16-byte vector of uint16 residuals / two of int32)
+          const double* m1 = sM1 + half * CW + cb;
 #pragma unroll
           for (int j = 0; j < 32; j += 16) {
             uint32_t lw[4];
@@ -440,12 +463,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
               const int jj = j + h * 8;
               int r[8];
               if constexpr (RES_ES == 2) {
-                const uint4 pr = *reinterpret_cast<const uint4*>(myrow + (cb + jj) * 2);
+                const uint4 pr = *reinterpret_cast<const uint4*>(myres + (cb + jj) * 2);
                 r[0] = pr.x & 0xFFFF; r[1] = pr.x >> 16; r[2] = pr.y & 0xFFFF; r[3] = pr.y >> 16;
                 r[4] = pr.z & 0xFFFF; r[5] = pr.z >> 16; r[6] = pr.w & 0xFFFF; r[7] = pr.w >> 16;
               } else {
-                const int4 pa = *reinterpret_cast<const int4*>(myrow + (cb + jj) * 4);
-                const int4 pb = *reinterpret_cast<const int4*>(myrow + (cb + jj) * 4 + 16);
+                const int4 pa = *reinterpret_cast<const int4*>(myres + (cb + jj) * 4);
+                const int4 pb = *reinterpret_cast<const int4*>(myres + (cb + jj) * 4 + 16);
                 r[0] = pa.x; r[1] = pa.y; r[2] = pa.z; r[3] = pa.w; r[4] = pb.x; r[5] = pb.y; r[6] = pb.z; r[7] = pb.w;
               }
               int y[8];
@@ -457,24 +480,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
                 const int v = __double2loint(qv);
                 const double dr = (RES_ES == 2) ? (__hiloint2double(0x43300000, r[k]) - kOffU)
                                                 : (__hiloint2double(0x43300000, r[k] ^ 0x80000000) - kOffS);
-                const double qr = __fma_rn(dr, m1[jj + k], kMagic);
+                const double qr = __fma_rn(dr, (EPI == TC_EPI_RES22) ? res_M : m1[jj + k], kMagic);
                 const int vr = __double2loint(qr);
+                const int sum = v + vr;
                 if constexpr (WIDE) {
                   ovf |= (__double2hiint(qv) + (int)((uint32_t)v >> 31)) ^ 0x43380000;
                   ovf |= (__double2hiint(qr) + (int)((uint32_t)vr >> 31)) ^ 0x43380000;
+                  ovf |= ((v ^ sum) & (vr ^ sum)) >> 31;                   // the sum itself wrapped
                 }
-                y[k] = max(sat_add(vr, v), relu_floor);
+                y[k] = max(sum, 0);
               }
               if (low_bits) {
+                int q[8];
 #pragma unroll
-                for (int g4 = 0; g4 < 2; ++g4) {
-                  int q[4];
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const double dl = __hiloint2double(0x43300000, y[g4 * 4 + k] ^ 0x80000000) - kOffS;
-                    q[k] = clampi(__double2loint(__fma_rn(dl, low_M, kMagic)), q_lo, q_hi);
-                  }
-                  lw[h * 2 + g4] = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+                for (int k = 0; k < 8; ++k) {                                 // y >= 0: unsigned conversion, no sign fix-up
+                  const double dl = __hiloint2double(0x43300000, y[k]) - kOffU;
+                  q[k] = clampi(__double2loint(__fma_rn(dl, low_M, kMagic)), q_lo, q_hi);
+                }
+                if (low_bits == 8) {
+                  lw[h * 2 + 0] = pack4(q[0], q[1], q[2], q[3]);
+                  lw[h * 2 + 1] = pack4(q[4], q[5], q[6], q[7]);
+                } else {
+                  lw[h] = pack_nibbles8(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7]));
                 }
               }
               if constexpr (Y_ES == 2) {
@@ -485,13 +512,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
                 o.y = __byte_perm(min(y[2], 65535), min(y[3], 65535), 0x5410);
                 o.z = __byte_perm(min(y[4], 65535), min(y[5], 65535), 0x5410);
                 o.w = __byte_perm(min(y[6], 65535), min(y[7], 65535), 0x5410);
-                *reinterpret_cast<uint4*>(myrow + (cb + jj) * 2) = o;   // in place: never ahead of the reads (2 B <= RES_ES)
+                *reinterpret_cast<uint4*>(myy + (cb + jj) * 2) = o;
               } else {
-                *reinterpret_cast<int4*>(myrow + (cb + jj) * 4) = make_int4(y[0], y[1], y[2], y[3]);
-                *reinterpret_cast<int4*>(myrow + (cb + jj) * 4 + 16) = make_int4(y[4], y[5], y[6], y[7]);
+                *reinterpret_cast<int4*>(myy + (cb + jj) * 4) = make_int4(y[0], y[1], y[2], y[3]);
+                *reinterpret_cast<int4*>(myy + (cb + jj) * 4 + 16) = make_int4(y[4], y[5], y[6], y[7]);
               }
             }
-            if (low_bits) *reinterpret_cast<uint4*>(mylow + cb + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            if (low_bits == 8) *reinterpret_cast<uint4*>(mylow + cb + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            else if (low_bits == 4) *reinterpret_cast<uint2*>(mylow + ((cb + j) >> 1)) = make_uint2(lw[0], lw[1]);
           }
         }
       }
@@ -501,49 +529,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       if (lane == 0) mbar_arrive(tempty_bar(buf));
       if (ew == 0) trace(2, tile_iter, 3);
 
-      // coalesced copy-out of the staged outputs (rows of this warp's lane quarter, its CW columns)
-      const int rows_ok = p.M - (m0 + quarter * 32);
-      if constexpr (Y_ES != 0) {
-        constexpr int CPR = CW * Y_ES / 16;
-        uint8_t* gy = reinterpret_cast<uint8_t*>(p.out) + ((size_t)(m0 + quarter * 32) * p.Cout + c0) * Y_ES;
-#pragma unroll
-        for (int i = 0; i < CPR; ++i) {
-          const int id = lane + i * 32;
-          const int rr = id / CPR, j = id % CPR;
-          if (rr < rows_ok)
-            *reinterpret_cast<int4*>(gy + (size_t)rr * p.Cout * Y_ES + j * 16) = *reinterpret_cast<const int4*>(slice + rr * PITCH + j * 16);
+      // asynchronous row stores: every lane hands its own row(s) to the bulk-copy engine (full 128-byte-line bursts)
+      fence_proxy_async();
+      const int grow = m0 + quarter * 32 + lane;
+      if (grow < p.M) {
+        if constexpr (Y_ES != 0)
+          bulk_store(reinterpret_cast<uint8_t*>(p.out) + ((size_t)grow * p.Cout + c0) * Y_ES, smem_u32(myy), CW * Y_ES);
+        if (low_bits) {
+          uint8_t* gl = reinterpret_cast<uint8_t*>(IS_RES ? p.out_low : p.out);
+          if (low_bits == 8) bulk_store(gl + (size_t)grow * p.Cout + c0, smem_u32(mylow), low_row_bytes);
+          else bulk_store(gl + (((size_t)grow * p.Cout + c0) >> 1), smem_u32(mylow), low_row_bytes);
         }
       }
-      if (low_bits == 8) {
-        constexpr int CPR = CW / 16;
-        uint8_t* gl = reinterpret_cast<uint8_t*>(IS_RES ? p.out_low : p.out) + (size_t)(m0 + quarter * 32) * p.Cout + c0;
-#pragma unroll
-        for (int i = 0; i < CPR; ++i) {
-          const int id = lane + i * 32;
-          const int rr = id / CPR, j = id % CPR;
-          if (rr < rows_ok)
-            *reinterpret_cast<int4*>(gl + (size_t)rr * p.Cout + j * 16) = *reinterpret_cast<const int4*>(lowslice + rr * S::LOW_PITCH + j * 16);
-        }
-      } else if (low_bits == 4) {   // 32 channels -> 16 packed bytes
-        constexpr int CPR = CW / 32;
-        uint8_t* gl = reinterpret_cast<uint8_t*>(IS_RES ? p.out_low : p.out) + (((size_t)(m0 + quarter * 32) * p.Cout + c0) >> 1);
-#pragma unroll
-        for (int i = 0; i < CPR; ++i) {
-          const int id = lane + i * 32;
-          const int rr = id / CPR, j = id % CPR;
-          if (rr < rows_ok) {
-            const uint4 a = *reinterpret_cast<const uint4*>(lowslice + rr * S::LOW_PITCH + j * 32);
-            const uint4 b = *reinterpret_cast<const uint4*>(lowslice + rr * S::LOW_PITCH + j * 32 + 16);
-            uint4 o;
-            o.x = pack_nibbles8(a.x, a.y); o.y = pack_nibbles8(a.z, a.w);
-            o.z = pack_nibbles8(b.x, b.y); o.w = pack_nibbles8(b.z, b.w);
-            *reinterpret_cast<uint4*>(gl + (((size_t)rr * p.Cout) >> 1) + j * 16) = o;
-          }
-        }
-      }
-      __syncwarp();   // slices are reused by the next tile
+      bulk_commit();
       if (ew == 0) trace(2, tile_iter, 4);
     }
+    bulk_wait_all();
     if constexpr (IS_RES) {
       cp_async_wait<0>();
       if (Y_ES == 2 && ymax > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
