@@ -216,33 +216,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
 
   if (warp < TC_PRODUCER_WARPS) {
     // =============================================================================== producers (128 threads)
-    const int row = tid;                       // A row of the tile owned by this thread
-    const uint32_t a_off = row * 64;           // row base; chunk c lives at a_off + ((c ^ a_sw) << 4)  (SWIZZLE_64B)
-    const uint32_t a_sw = (row >> 1) & 3;
+    // Coalesced gather: consecutive lanes cover one row's bytes (4 lanes x 16 B = 64 B int8 row, 2 lanes x 16 B = packed
+    // 4-bit row), so a warp-level cp.async touches 8 (16) cache lines instead of 32.  Each thread serves A_PASSES rows.
+    constexpr int A_LPR = A4 ? 2 : 4;                       // lanes (= 16-byte chunks) per A row in global memory
+    constexpr int A_PASSES = A_LPR;                         // rows per thread: 128 rows * A_LPR chunks / 128 threads
+    const int a_ch = tid % A_LPR;
     uint32_t it = 0;                           // global k-tile counter (ring position)
     uint32_t pending = 0;                      // k-tiles issued but not yet signalled
-    // A4: expand this thread's packed row of k-tile j (64 nibbles) into the int8 A tile of that k-tile's stage
-    auto expand_row = [&](uint32_t j) {
-      const uint8_t* stg = smem + S::STG_OFF + (j % (LAG + 1)) * S::STG_SLOT + row * 32;
-      uint8_t* dst = smem + (j % STAGES) * S::STAGE + a_off;
+    // A4: expand the 16 packed bytes (one 32-channel block) this thread loaded for each of its rows of k-tile j
+    auto expand_rows = [&](uint32_t j) {
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {      // 32 channels = 16 packed bytes -> 32 int8 = chunks 2*blk, 2*blk+1
-        const uint4 w = *reinterpret_cast<const uint4*>(stg + blk * 16);
+      for (int i = 0; i < A_PASSES; ++i) {
+        const int row = tid / A_LPR + i * (128 / A_LPR);
+        const uint32_t sw = (row >> 1) & 3;
+        const uint4 w = *reinterpret_cast<const uint4*>(smem + S::STG_OFF + (j % (LAG + 1)) * S::STG_SLOT + row * 32 + a_ch * 16);
+        uint8_t* dst = smem + (j % STAGES) * S::STAGE + row * 64;
         const uint4 lo = make_uint4(w.x & 0x0F0F0F0Fu, w.y & 0x0F0F0F0Fu, w.z & 0x0F0F0F0Fu, w.w & 0x0F0F0F0Fu);
         const uint4 hi = make_uint4((w.x >> 4) & 0x0F0F0F0Fu, (w.y >> 4) & 0x0F0F0F0Fu, (w.z >> 4) & 0x0F0F0F0Fu, (w.w >> 4) & 0x0F0F0F0Fu);
-        *reinterpret_cast<uint4*>(dst + (((2 * blk) ^ a_sw) << 4)) = lo;
-        *reinterpret_cast<uint4*>(dst + (((2 * blk + 1) ^ a_sw) << 4)) = hi;
+        *reinterpret_cast<uint4*>(dst + (((2 * a_ch) ^ sw) << 4)) = lo;
+        *reinterpret_cast<uint4*>(dst + (((2 * a_ch + 1) ^ sw) << 4)) = hi;
       }
     };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-      const int m = m0 + row;
-      const bool a_ok = m < p.M;
-      const int mm = a_ok ? m : 0;
-      const int n = mm / (p.Ho * p.Wo);
-      const int r = mm - n * (p.Ho * p.Wo);
-      const int ho = r / p.Wo, wo = r - ho * p.Wo;
-      const int hi0 = ho * p.stride - p.pad, wi0 = wo * p.stride - p.pad, pix = n * p.H * p.W;
+      int hi0[A_PASSES], wi0[A_PASSES], pix[A_PASSES];
+      bool a_ok[A_PASSES];
+#pragma unroll
+      for (int i = 0; i < A_PASSES; ++i) {
+        const int m = m0 + tid / A_LPR + i * (128 / A_LPR);
+        a_ok[i] = m < p.M;
+        const int mm = a_ok[i] ? m : 0;
+        const int n = mm / (p.Ho * p.Wo);
+        const int r = mm - n * (p.Ho * p.Wo);
+        const int ho = r / p.Wo, wo = r - ho * p.Wo;
+        hi0[i] = ho * p.stride - p.pad;
+        wi0[i] = wo * p.stride - p.pad;
+        pix[i] = n * p.H * p.W;
+      }
       const int8_t* wrow = p.w + (size_t)n0 * p.K;
       int c = 0, kw = 0, kh = 0;
       const uint32_t ptile = (tile - blockIdx.x) / gridDim.x;
@@ -253,20 +263,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         if (warp == 0 && kt == 0) trace(0, ptile, 1);
         const uint32_t a_base = smem_base + stage * S::STAGE;
         const uint32_t b_base = a_base + S::A_STAGE;
-        {
-          const int hi = hi0 + kh, wi = wi0 + kw;
-          const bool v = a_ok && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W;
-          const int nb = v ? 16 : 0;
-          if constexpr (!A4) {
-            const uint8_t* src = v ? p.x + (size_t)(pix + hi * p.W + wi) * p.x_pix_bytes + c * 64 : p.x;
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) cp_async_16(a_base + a_off + ((ch ^ a_sw) << 4), src + ch * 16, nb);
-          } else {
-            const uint8_t* src = v ? p.x + (size_t)(pix + hi * p.W + wi) * p.x_pix_bytes + c * 32 : p.x;
-            const uint32_t stg = smem_base + S::STG_OFF + (it % (LAG + 1)) * S::STG_SLOT + row * 32;
-            cp_async_16(stg, src, nb);
-            cp_async_16(stg + 16, src + 16, nb);
-          }
+        for (int i = 0; i < A_PASSES; ++i) {
+          const int row = tid / A_LPR + i * (128 / A_LPR);
+          const int hi = hi0[i] + kh, wi = wi0[i] + kw;
+          const bool v = a_ok[i] && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W;
+          const uint8_t* src = v ? p.x + (size_t)(pix[i] + hi * p.W + wi) * p.x_pix_bytes + c * (A4 ? 32 : 64) + a_ch * 16 : p.x;
+          if constexpr (!A4) cp_async_16(a_base + swz<64>(row, a_ch), src, v ? 16 : 0);
+          else cp_async_16(smem_base + S::STG_OFF + (it % (LAG + 1)) * S::STG_SLOT + row * 32 + a_ch * 16, src, v ? 16 : 0);
         }
 #pragma unroll
         for (int i = 0; i < BN / 32; ++i) {     // B: BN rows x 4 chunks over 128 threads
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         ++pending;
         if (pending > LAG) {                    // the group issued LAG iterations ago has landed
           cp_async_wait<LAG>();
-          if constexpr (A4) expand_row(it - LAG);
+          if constexpr (A4) expand_rows(it - LAG);
           fence_proxy_async();
           mbar_arrive(full_bar((it - LAG) % STAGES));
           --pending;
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     // drain
     cp_async_wait<0>();
     if constexpr (A4)
-      for (uint32_t j = pending; j > 0; --j) expand_row(it - j);
+      for (uint32_t j = pending; j > 0; --j) expand_rows(it - j);
     fence_proxy_async();
     for (uint32_t j = pending; j > 0; --j) mbar_arrive(full_bar((it - j) % STAGES));
   } else if (warp == TC_MMA_WARP) {
@@ -399,9 +403,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         const int nxt = tile + gridDim.x;
         if (nxt < num_tiles) prefetch_residual(nxt, slice0 + ((tile_iter + 1) & 1) * S::SLICE);
         else cp_async_commit();
-      } else if constexpr (IS_RES) {        // in-place variant: the previous tile's row stores must have left the buffer
-        bulk_wait_read_all();
-        __syncwarp();
+      } else if constexpr (IS_RES) {        // in-place variant (copy-out of the previous tile is synchronous)
         prefetch_residual(tile, rslice);
       }
 
@@ -413,7 +415,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         if constexpr (EPI == TC_EPI_RES22) cp_async_wait<1>();
         else cp_async_wait<0>();
       }
-      bulk_wait_read_all();            // the bulk stores of the previous tile have finished reading yslice / lowslice
       __syncwarp();
       const uint8_t* myres = rslice + lane * PITCH;
       if (ew == 0) trace(2, tile_iter, 2);
@@ -529,22 +530,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       if (lane == 0) mbar_arrive(tempty_bar(buf));
       if (ew == 0) trace(2, tile_iter, 3);
 
-      // asynchronous row stores: every lane hands its own row(s) to the bulk-copy engine (full 128-byte-line bursts)
-      fence_proxy_async();
-      const int grow = m0 + quarter * 32 + lane;
-      if (grow < p.M) {
-        if constexpr (Y_ES != 0)
-          bulk_store(reinterpret_cast<uint8_t*>(p.out) + ((size_t)grow * p.Cout + c0) * Y_ES, smem_u32(myy), CW * Y_ES);
-        if (low_bits) {
-          uint8_t* gl = reinterpret_cast<uint8_t*>(IS_RES ? p.out_low : p.out);
-          if (low_bits == 8) bulk_store(gl + (size_t)grow * p.Cout + c0, smem_u32(mylow), low_row_bytes);
-          else bulk_store(gl + (((size_t)grow * p.Cout + c0) >> 1), smem_u32(mylow), low_row_bytes);
+      // coalesced copy-out of the staged outputs: a warp instruction writes whole rows (4 rows x 128 B for uint16 tiles);
+      // all shared-memory reads are issued before the first global store
+      const int rows_ok = p.M - (m0 + quarter * 32);
+      if constexpr (Y_ES != 0) {
+        constexpr int CPR = CW * Y_ES / 16;
+        uint8_t* gy = reinterpret_cast<uint8_t*>(p.out) + ((size_t)(m0 + quarter * 32) * p.Cout + c0) * Y_ES;
+        int4 v[CPR];
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+          const int id = lane + i * 32;
+          v[i] = *reinterpret_cast<const int4*>(yslice + (id / CPR) * PITCH + (id % CPR) * 16);
+        }
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+          const int id = lane + i * 32;
+          if (id / CPR < rows_ok) *reinterpret_cast<int4*>(gy + (size_t)(id / CPR) * p.Cout * Y_ES + (id % CPR) * 16) = v[i];
         }
       }
-      bulk_commit();
+      if (low_bits == 8) {
+        constexpr int CPR = CW / 16;
+        uint8_t* gl = reinterpret_cast<uint8_t*>(IS_RES ? p.out_low : p.out) + (size_t)(m0 + quarter * 32) * p.Cout + c0;
+        int4 v[CPR];
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+          const int id = lane + i * 32;
+          v[i] = *reinterpret_cast<const int4*>(lowslice + (id / CPR) * S::LOW_PITCH + (id % CPR) * 16);
+        }
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+          const int id = lane + i * 32;
+          if (id / CPR < rows_ok) *reinterpret_cast<int4*>(gl + (size_t)(id / CPR) * p.Cout + (id % CPR) * 16) = v[i];
+        }
+      } else if (low_bits == 4) {   // rows of CW / 2 packed bytes
+        constexpr int CPR = CW / 32;
+        uint8_t* gl = reinterpret_cast<uint8_t*>(IS_RES ? p.out_low : p.out) + (((size_t)(m0 + quarter * 32) * p.Cout + c0) >> 1);
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+          const int id = lane + i * 32;
+          const int rr = id / CPR, j = id % CPR;
+          if (rr < rows_ok)
+            *reinterpret_cast<int4*>(gl + (((size_t)rr * p.Cout) >> 1) + j * 16) = *reinterpret_cast<const int4*>(lowslice + rr * S::LOW_PITCH + j * 16);
+        }
+      }
+      __syncwarp();   // staging slices are rewritten by the next tile
       if (ew == 0) trace(2, tile_iter, 4);
     }
-    bulk_wait_all();
     if constexpr (IS_RES) {
       cp_async_wait<0>();
       if (Y_ES == 2 && ymax > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
