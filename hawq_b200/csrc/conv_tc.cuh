@@ -89,6 +89,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
   __trap();
 }
+// the mbarrier arrives (count not incremented) once all cp.async operations previously issued by this thread have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -278,14 +282,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
           const int brow = id >> 2, ch = id & 3;
           cp_async_16(b_base + swz<64>(brow, ch), wrow + (size_t)brow * p.K + kt * 64 + ch * 16, 16);
         }
-        cp_async_commit();
-        ++pending;
-        if (pending > LAG) {                    // the group issued LAG iterations ago has landed
-          cp_async_wait<LAG>();
-          if constexpr (A4) expand_rows(it - LAG);
-          fence_proxy_async();
-          mbar_arrive(full_bar((it - LAG) % STAGES));
-          --pending;
+        if constexpr (!A4) {
+          // int8 rows need no post-processing: the barrier is signalled by the copy hardware itself, the producer never
+          // waits for data (the MMA thread issues the generic->async proxy fence after its barrier wait)
+          cp_async_mbar_arrive_noinc(full_bar(stage));
+        } else {
+          cp_async_commit();
+          ++pending;
+          if (pending > LAG) {                  // the group issued LAG iterations ago has landed: expand it
+            cp_async_wait<LAG>();
+            expand_rows(it - LAG);
+            fence_proxy_async();
+            mbar_arrive(full_bar((it - LAG) % STAGES));
+            --pending;
+          }
         }
         if (++c == p.cin_chunks) { c = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
       }
@@ -312,6 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         for (int kt = 0; kt < KT; ++kt, ++it) {
           const int stage = it % STAGES;
           mbar_wait(full_bar(stage), (it / STAGES) & 1);
+          fence_proxy_async();            // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
           tc_fence_after();
           if (kt == 0) trace(1, tile_iter, 2);
           const uint32_t a_addr = smem_base + stage * S::STAGE;
