@@ -23,6 +23,34 @@ struct hawq_handle {
 static thread_local char g_err[512] = "";
 static long long* g_trace = nullptr;   // hawq_debug_set_trace
 
+// ---- TMA tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return reinterpret_cast<encode_tiled_fn>(ptr);
+  }();
+  return fn;
+}
+// byte matrix [rows][inner_bytes] with row pitch pitch_bytes; box = box_inner bytes x box_rows rows
+static int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner_bytes, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
+                       uint32_t box_rows, CUtensorMapSwizzle sw) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return -1;
+  const cuuint64_t dims[2] = {inner_bytes, rows};
+  const cuuint64_t strides[1] = {pitch_bytes};
+  const cuuint32_t box[2] = {box_inner, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -1;
+}
+
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -82,21 +110,21 @@ static int set_tc_attr() {
 }
 
 template <int EPI, bool WIDE, bool A4>
-static void launch_tc2(const ConvParams& p, bool bn128, int grid, cudaStream_t st) {
-  if (bn128) conv_tc_kernel<128, EPI, WIDE, A4><<<grid, TC_THREADS, TcSmem<128, EPI, A4>::TOTAL, st>>>(p);
-  else conv_tc_kernel<64, EPI, WIDE, A4><<<grid, TC_THREADS, TcSmem<64, EPI, A4>::TOTAL, st>>>(p);
+static void launch_tc2(const ConvParams& p, const TcMaps& maps, bool bn128, int grid, cudaStream_t st) {
+  if (bn128) conv_tc_kernel<128, EPI, WIDE, A4><<<grid, TC_THREADS, TcSmem<128, EPI, A4>::TOTAL, st>>>(p, maps);
+  else conv_tc_kernel<64, EPI, WIDE, A4><<<grid, TC_THREADS, TcSmem<64, EPI, A4>::TOTAL, st>>>(p, maps);
 }
 template <int EPI>
-static void launch_tc(const ConvParams& p, bool bn128, bool ratios_wide, bool a4, int grid, cudaStream_t st) {
+static void launch_tc(const ConvParams& p, const TcMaps& maps, bool bn128, bool ratios_wide, bool a4, int grid, cudaStream_t st) {
   if constexpr (EPI >= TC_EPI_RES22) {
     if (ratios_wide) {
-      if (a4) launch_tc2<EPI, true, true>(p, bn128, grid, st);
-      else launch_tc2<EPI, true, false>(p, bn128, grid, st);
+      if (a4) launch_tc2<EPI, true, true>(p, maps, bn128, grid, st);
+      else launch_tc2<EPI, true, false>(p, maps, bn128, grid, st);
       return;
     }
   }
-  if (a4) launch_tc2<EPI, false, true>(p, bn128, grid, st);
-  else launch_tc2<EPI, false, false>(p, bn128, grid, st);
+  if (a4) launch_tc2<EPI, false, true>(p, maps, bn128, grid, st);
+  else launch_tc2<EPI, false, false>(p, maps, bn128, grid, st);
 }
 
 template <int BN, bool A4>
@@ -197,6 +225,8 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   p.low_lo = ep->low_lo; p.low_hi = ep->low_hi; p.cout_store = ep->cout_store;
   p.slow_scalar = 0;
   p.trace = g_trace;
+  p.tma_a = 0;
+  p.tma_io = 0;
   if (ep->mode == HAWQ_EPI_RESIDUAL) {
     if (ep->res_kind == 0 && !dyadic_is_fast(ep->res_m, ep->res_e)) p.slow_scalar = 1;
     if (ep->low_bits != 0 && !dyadic_is_fast(ep->low_m, ep->low_e)) p.slow_scalar = 1;
@@ -248,17 +278,25 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   const bool ratios_wide = !ratios_one && (ep->flags & HAWQ_EP_RATIOS_LE_2P20) != 0 && ep->mode == HAWQ_EPI_RESIDUAL;
   if (tc_enabled && tc_epi && (ratios_one || ratios_wide)) {
     const bool a4 = d->a_bits == 4;
+    const int bn = (d->Cout % 128 == 0) ? 128 : 64;
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    if (make_map_2d(&maps.b, w, (uint64_t)p.K, (uint64_t)d->Cout, (uint64_t)p.K, 64, (uint32_t)bn, CU_TENSOR_MAP_SWIZZLE_64B))
+      return fail(HAWQ_ERR_CUDA, "hawq_conv2d: cuTensorMapEncodeTiled (weights) failed");
+    p.tma_a = (!a4 && d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0) ? 1 : 0;
+    if (p.tma_a && make_map_2d(&maps.a, x, (uint64_t)d->Cin, (uint64_t)M, (uint64_t)d->Cin, 64, TC_BM, CU_TENSOR_MAP_SWIZZLE_64B))
+      return fail(HAWQ_ERR_CUDA, "hawq_conv2d: cuTensorMapEncodeTiled (activations) failed");
     const bool wide = (d->Cout % 128 == 0);
     const long long tiles = ((M + TC_BM - 1) / TC_BM) * (d->Cout / (wide ? 128 : 64));
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
     cudaStream_t st = (cudaStream_t)stream;
-    if (ep->mode == HAWQ_EPI_REQUANT) launch_tc<TC_EPI_REQ>(p, wide, false, a4, grid, st);
-    else if (ep->mode == HAWQ_EPI_RAW_I32) launch_tc<TC_EPI_RAW>(p, wide, false, a4, grid, st);
+    if (ep->mode == HAWQ_EPI_REQUANT) launch_tc<TC_EPI_REQ>(p, maps, wide, false, a4, grid, st);
+    else if (ep->mode == HAWQ_EPI_RAW_I32) launch_tc<TC_EPI_RAW>(p, maps, wide, false, a4, grid, st);
     else {
       const int res_es = (ep->res_kind == 1 || ep->res_bits == 32) ? 4 : 2;
-      if (res_es == 2 && ep->y_bits == 16) launch_tc<TC_EPI_RES22>(p, wide, ratios_wide, a4, grid, st);
-      else if (res_es == 4 && ep->y_bits == 32) launch_tc<TC_EPI_RES44>(p, wide, ratios_wide, a4, grid, st);
-      else if (res_es == 4 && ep->y_bits == 16) launch_tc<TC_EPI_RES42>(p, wide, ratios_wide, a4, grid, st);
+      if (res_es == 2 && ep->y_bits == 16) launch_tc<TC_EPI_RES22>(p, maps, wide, ratios_wide, a4, grid, st);
+      else if (res_es == 4 && ep->y_bits == 32) launch_tc<TC_EPI_RES44>(p, maps, wide, ratios_wide, a4, grid, st);
+      else if (res_es == 4 && ep->y_bits == 16) launch_tc<TC_EPI_RES42>(p, maps, wide, ratios_wide, a4, grid, st);
       else goto legacy;   // uint16 residual in, int32 out: not a combination the engine produces
     }
     return launch_check("conv_tc");

@@ -40,6 +40,8 @@ struct ConvParams {
   int low_e, low_lo, low_hi;
   int cout_store;
   int slow_scalar;   // host-checked: a scalar dyadic pair (res / low) has ratio > 1 -> generic 64-bit requant
+  int tma_a;         // tcgen05 kernel: activations are fetched by TMA (1x1 stride-1 int8 layers)
+  int tma_io;        // tcgen05 kernel: uint16 residual tile in / outputs out through TMA
   long long* trace;  // debug timeline (hawq_debug_set_trace): [role][tile][event] clock64 values of CTA 0, or null
 };
 

@@ -17,10 +17,21 @@
 // HAWQ_FLAG_BAD_RATIO in the status word instead of producing wrong numbers).  Everything else uses conv_igemm.cuh.
 // Every mbarrier wait is bounded: a protocol bug traps (launch failure) instead of hanging the GPU.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 #include "conv_igemm.cuh"
 
 namespace hawq {
+
+// TMA tensor maps of one launch (passed as a __grid_constant__ kernel parameter)
+struct alignas(64) TcMaps {
+  CUtensorMap b;     // weights  [Cout][K] int8, box 64 x BN, SWIZZLE_64B
+  CUtensorMap a;     // activations as a matrix [M][Cin] int8 (1x1 stride-1 layers), box 64 x 128, SWIZZLE_64B
+  CUtensorMap res;   // uint16 residual stream [M][Cout], box (CW * 2 bytes) x 32 rows, SWIZZLE_128B
+  CUtensorMap y;     // uint16 residual stream out, same shape
+  CUtensorMap low;   // low-bit activation out [M][Cout * bits / 8], box (CW * bits / 8) x 32 rows
+};
 
 constexpr int TC_BM = 128;
 constexpr int TC_PRODUCER_WARPS = 4;
@@ -92,6 +103,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // the mbarrier arrives (count not incremented) once all cp.async operations previously issued by this thread have landed
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA: 2-D tiled box global -> shared, completion (bytes) on an mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// TMA: 2-D tiled box shared -> global (bulk async group)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_src) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -171,7 +195,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n, bool a_signed
 // Preconditions (promised via HAWQ_EP_RATIOS_*, re-checked -> HAWQ_FLAG_BAD_RATIO): ratios within the bound,
 // |bias| < 2^29 (sums of two requantised terms then cannot wrap), RESIDUAL launches have relu = 1.
 template <int BN, int EPI, bool WIDE, bool A4>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams p, const __grid_constant__ TcMaps maps) {
   using S = TcSmem<BN, EPI, A4>;
   constexpr int BM = TC_BM, STAGES = S::STAGES, LAG = S::LAG;
   constexpr int CW = S::CW;                      // columns handled by one epilogue warp: 32 or 64
@@ -203,7 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   // ---- one-time setup ----
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), TC_PRODUCER_WARPS * 32);
+      mbar_init(full_bar(s), p.tma_a ? 1 : TC_PRODUCER_WARPS * 32 + 1);   // + the expect_tx arrival of the TMA-issuing thread
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -225,6 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     constexpr int A_LPR = A4 ? 2 : 4;                       // lanes (= 16-byte chunks) per A row in global memory
     constexpr int A_PASSES = A_LPR;                         // rows per thread: 128 rows * A_LPR chunks / 128 threads
     const int a_ch = tid % A_LPR;
+    const bool tma_a = !A4 && p.tma_a != 0;    // activations by TMA: only thread 0 works in this role
     uint32_t it = 0;                           // global k-tile counter (ring position)
     uint32_t pending = 0;                      // k-tiles issued but not yet signalled
     // A4: expand the 16 packed bytes (one 32-channel block) this thread loaded for each of its rows of k-tile j
@@ -241,6 +266,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         *reinterpret_cast<uint4*>(dst + (((2 * a_ch + 1) ^ sw) << 4)) = hi;
       }
     };
+    if (tma_a) {
+      if (tid == 0) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+          for (int kt = 0; kt < KT; ++kt, ++it) {
+            const int stage = it % STAGES;
+            mbar_wait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
+            const uint32_t a_base = smem_base + stage * S::STAGE;
+            mbar_arrive_expect_tx(full_bar(stage), S::A_STAGE + S::B_STAGE);
+            tma_load_2d(a_base, &maps.a, kt * 64, m0, full_bar(stage));
+            tma_load_2d(a_base + S::A_STAGE, &maps.b, kt * 64, n0, full_bar(stage));
+          }
+        }
+      }
+    } else {
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       int hi0[A_PASSES], wi0[A_PASSES], pix[A_PASSES];
@@ -257,7 +297,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         wi0[i] = wo * p.stride - p.pad;
         pix[i] = n * p.H * p.W;
       }
-      const int8_t* wrow = p.w + (size_t)n0 * p.K;
       int c = 0, kw = 0, kh = 0;
       const uint32_t ptile = (tile - blockIdx.x) / gridDim.x;
       if (warp == 0) trace(0, ptile, 0);
@@ -276,11 +315,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
           if constexpr (!A4) cp_async_16(a_base + swz<64>(row, a_ch), src, v ? 16 : 0);
           else cp_async_16(smem_base + S::STG_OFF + (it % (LAG + 1)) * S::STG_SLOT + row * 32 + a_ch * 16, src, v ? 16 : 0);
         }
-#pragma unroll
-        for (int i = 0; i < BN / 32; ++i) {     // B: BN rows x 4 chunks over 128 threads
-          const int id = tid + i * 128;
-          const int brow = id >> 2, ch = id & 3;
-          cp_async_16(b_base + swz<64>(brow, ch), wrow + (size_t)brow * p.K + kt * 64 + ch * 16, 16);
+        if (tid == 0) {                         // weights: one TMA box (64 x BN, SWIZZLE_64B) per k-tile
+          mbar_arrive_expect_tx(full_bar(stage), S::B_STAGE);
+          tma_load_2d(b_base, &maps.b, kt * 64, n0, full_bar(stage));
         }
         if constexpr (!A4) {
           // int8 rows need no post-processing: the barrier is signalled by the copy hardware itself, the producer never
@@ -307,6 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       for (uint32_t j = pending; j > 0; --j) expand_rows(it - j);
     fence_proxy_async();
     for (uint32_t j = pending; j > 0; --j) mbar_arrive(full_bar((it - j) % STAGES));
+    }
   } else if (warp == TC_MMA_WARP) {
     // =============================================================================== MMA issuer (one lane)
     if (lane == 0) {

@@ -55,6 +55,8 @@ CONV_GEOMS = [
     (2, 9, 9, 256, 256, 1, 2, 0),
     (1, 20, 12, 64, 192, 3, 1, 1),     # Cout = 192 -> BN = 64 path with 3 column tiles
     (5, 6, 6, 128, 128, 3, 1, 1),
+    (3, 7, 7, 128, 128, 1, 1, 0),      # 1x1 stride 1, M = 147: TMA-fed activations with a ragged (zero-filled) last tile
+    (2, 5, 5, 192, 256, 1, 1, 0),      # M = 50 < one tile, K = 3 k-tiles
 ]
 
 
@@ -115,7 +117,7 @@ def test_conv_requant_ties_and_generic_path(ratio_kind):
 
 @pytest.mark.parametrize("tc", [0, 1])
 @pytest.mark.parametrize("a_bits", [8, 4])
-@pytest.mark.parametrize("geom", CONV_GEOMS[:4])
+@pytest.mark.parametrize("geom", CONV_GEOMS[:4] + CONV_GEOMS[6:])
 def test_conv_residual(geom, a_bits, tc):
     n, h, w, cin, cout, k, s, p = geom
     r = rng(sum(v * (i + 5) for i, v in enumerate(geom)) * 8 + a_bits + 1)
