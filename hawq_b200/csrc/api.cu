@@ -290,6 +290,19 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
     const long long tiles = ((M + TC_BM - 1) / TC_BM) * (d->Cout / (wide ? 128 : 64));
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
     cudaStream_t st = (cudaStream_t)stream;
+    if (ep->mode == HAWQ_EPI_RESIDUAL && ep->res_kind == 0 && ep->res_bits == 16 && ep->y_bits == 16) {
+      const uint32_t cw = bn / 2;   // columns per epilogue warp
+      const CUtensorMapSwizzle sw_y = cw * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+      int bad = make_map_2d(&maps.res, res, (uint64_t)d->Cout * 2, (uint64_t)M, (uint64_t)d->Cout * 2, cw * 2, 32, sw_y);
+      bad |= make_map_2d(&maps.y, out, (uint64_t)d->Cout * 2, (uint64_t)M, (uint64_t)d->Cout * 2, cw * 2, 32, sw_y);
+      if (ep->low_bits) {
+        const uint32_t lb = cw * ep->low_bits / 8;   // low tile row bytes: 64 / 32 / 16
+        const CUtensorMapSwizzle sw_l = lb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : lb == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+        bad |= make_map_2d(&maps.low, out_low, (uint64_t)d->Cout * ep->low_bits / 8, (uint64_t)M, (uint64_t)d->Cout * ep->low_bits / 8, lb, 32, sw_l);
+      }
+      if (bad) return fail(HAWQ_ERR_CUDA, "hawq_conv2d: cuTensorMapEncodeTiled (residual epilogue) failed");
+      p.tma_io = 1;
+    }
     if (ep->mode == HAWQ_EPI_REQUANT) launch_tc<TC_EPI_REQ>(p, maps, wide, false, a4, grid, st);
     else if (ep->mode == HAWQ_EPI_RAW_I32) launch_tc<TC_EPI_RAW>(p, maps, wide, false, a4, grid, st);
     else {

@@ -60,11 +60,12 @@ struct TcSmem {
   static constexpr int RES_ES = (EPI == TC_EPI_RES22) ? 2 : (EPI >= TC_EPI_RES44 ? 4 : 0);
   static constexpr int Y_ES = (EPI == TC_EPI_RES22 || EPI == TC_EPI_RES42) ? 2 : ((EPI == TC_EPI_RES44 || EPI == TC_EPI_RAW) ? 4 : 0);
   static constexpr int SLICE_ES = RES_ES > Y_ES ? RES_ES : Y_ES;
-  static constexpr int SLICE_PITCH = CW * SLICE_ES + 16;                   // +16 B: 16-byte row-per-lane accesses conflict-free
-  static constexpr int SLICE = SLICE_ES ? 32 * SLICE_PITCH : 0;
+  static constexpr bool TMA_IO = (EPI == TC_EPI_RES22);                    // residual tile in / outputs out as swizzled TMA boxes
+  static constexpr int SLICE_PITCH = TMA_IO ? CW * SLICE_ES : CW * SLICE_ES + 16;   // padded: 16-byte row-per-lane accesses conflict-free
+  static constexpr int SLICE = SLICE_ES ? (TMA_IO ? 4096 : 32 * SLICE_PITCH) : 0;
   static constexpr int SLICE_BUFS = (EPI == TC_EPI_RES22) ? 3 : 1;         // RES22: 2 prefetch + 1 output; RES4x: in place; RAW: output
-  static constexpr int LOW_PITCH = CW + 16;
-  static constexpr int LOW_SLICE = (EPI == TC_EPI_RAW) ? 0 : 32 * LOW_PITCH;
+  static constexpr int LOW_PITCH = TMA_IO ? CW : CW + 16;
+  static constexpr int LOW_SLICE = (EPI == TC_EPI_RAW) ? 0 : (TMA_IO ? 2048 : 32 * LOW_PITCH);   // TMA boxes keep 1024 B alignment
   static constexpr int SLICES_OFF = RING;
   static constexpr int LOW_OFF = SLICES_OFF + TC_EPI_WARPS * SLICE * SLICE_BUFS;
   static constexpr int CST_OFF = LOW_OFF + TC_EPI_WARPS * LOW_SLICE;       // double2 {Cb, M}[BN]
@@ -72,7 +73,7 @@ struct TcSmem {
   static constexpr int STG_SLOT = TC_BM * 32;                              // packed 4-bit rows of one k-tile (A4 only)
   static constexpr int STG_OFF = M1_OFF + BN * 8;
   static constexpr int BAR_OFF = STG_OFF + (A4 ? (LAG + 1) * STG_SLOT : 0);   // mbarriers + tmem base
-  static constexpr int TOTAL = BAR_OFF + 512 + 1024;                       // + slack for 1024 B alignment of the ring
+  static constexpr int TOTAL = BAR_OFF + 1024 + 1024;                       // + slack for 1024 B alignment of the ring
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
@@ -175,6 +176,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// dense row-major tile written / read by TMA with the swizzle mode matching its row length (128/64/32/16 B rows ->
+// SWIZZLE_128B/64B/32B/NONE): byte offset of 16-byte chunk j of row l
+__device__ __forceinline__ uint32_t tma_tile_off(int row_bytes, int l, int j) {
+  const int x = row_bytes == 128 ? (l & 7) : row_bytes == 64 ? ((l >> 1) & 3) : row_bytes == 32 ? ((l >> 2) & 1) : 0;
+  return (uint32_t)(l * row_bytes + ((j ^ x) << 4));
+}
+
 // UMMA shared-memory descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row atoms of 512 B (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
@@ -214,6 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::BAR_OFF + 8 * (2 * STAGES + 4));
+  auto res_bar = [&](int ew_, int b) { return bar_base + 8u * (2 * STAGES + 6 + ew_ * 2 + b); };   // TMA residual tiles (per epilogue warp)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // debug timeline: role 0 producer (warp 0), 1 MMA, 2 epilogue (first epilogue warp); 8 events x 64 tiles per role
@@ -233,6 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), TC_EPI_WARPS);
+      for (int w = 0; w < TC_EPI_WARPS; ++w) mbar_init(res_bar(w, b), 1);
     }
     fence_barrier_init();
   }
@@ -400,6 +410,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     if (IS_RES && p.res_kind == 0) bad |= !ratio_ok(p.res_m, p.res_e);
     if (low_bits && IS_RES) bad |= !dyadic_is_fast(p.low_m, p.low_e);
 
+    constexpr int RB = CW * 2;                  // RES22 tile row bytes (uint16)
+    auto prefetch_residual_tma = [&](int tile, uint32_t k) {      // k-th tile of this CTA -> buffer k & 1
+      if (lane == 0) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        mbar_arrive_expect_tx(res_bar(ew, k & 1), 32 * RB);
+        tma_load_2d(smem_u32(slice0 + (k & 1) * S::SLICE), &maps.res, (n0 + half * CW) * 2, m0 + quarter * 32, res_bar(ew, k & 1));
+      }
+    };
     auto prefetch_residual = [&](int tile, uint8_t* dst) {
       if constexpr (IS_RES) {
         const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
@@ -419,7 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     auto pack4 = [](int a, int b, int c, int d) { return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410); };
 
     if constexpr (EPI == TC_EPI_RES22) {
-      if ((int)blockIdx.x < num_tiles) prefetch_residual(blockIdx.x, slice0);
+      if ((int)blockIdx.x < num_tiles) prefetch_residual_tma(blockIdx.x, 0);
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
@@ -450,8 +468,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
 
       if constexpr (EPI == TC_EPI_RES22) {         // this tile's residual was prefetched; start the next one
         const int nxt = tile + gridDim.x;
-        if (nxt < num_tiles) prefetch_residual(nxt, slice0 + ((tile_iter + 1) & 1) * S::SLICE);
-        else cp_async_commit();
+        if (nxt < num_tiles) prefetch_residual_tma(nxt, tile_iter + 1);
       } else if constexpr (IS_RES) {        // in-place variant (copy-out of the previous tile is synchronous)
         prefetch_residual(tile, rslice);
       }
@@ -460,9 +477,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       mbar_wait(tfull_bar(buf), (tile_iter >> 1) & 1);
       tc_fence_after();
       if (ew == 0) trace(2, tile_iter, 1);
-      if constexpr (IS_RES) {
-        if constexpr (EPI == TC_EPI_RES22) cp_async_wait<1>();
-        else cp_async_wait<0>();
+      if constexpr (EPI == TC_EPI_RES22) {
+        mbar_wait(res_bar(ew, tile_iter & 1), (tile_iter >> 1) & 1);     // residual tile landed (TMA)
+        if (lane == 0) bulk_wait_read_all();                            // previous tile's TMA stores have read y / low tiles
+      } else if constexpr (IS_RES) {
+        cp_async_wait<0>();
       }
       __syncwarp();
       const uint8_t* myres = rslice + lane * PITCH;
@@ -513,7 +532,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
               const int jj = j + h * 8;
               int r[8];
               if constexpr (RES_ES == 2) {
-                const uint4 pr = *reinterpret_cast<const uint4*>(myres + (cb + jj) * 2);
+                const uint4 pr = *reinterpret_cast<const uint4*>(rslice + tma_tile_off(RB, lane, (cb + jj) >> 3));
                 r[0] = pr.x & 0xFFFF; r[1] = pr.x >> 16; r[2] = pr.y & 0xFFFF; r[3] = pr.y >> 16;
                 r[4] = pr.z & 0xFFFF; r[5] = pr.z >> 16; r[6] = pr.w & 0xFFFF; r[7] = pr.w >> 16;
               } else {
@@ -562,14 +581,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
                 o.y = __byte_perm(min(y[2], 65535), min(y[3], 65535), 0x5410);
                 o.z = __byte_perm(min(y[4], 65535), min(y[5], 65535), 0x5410);
                 o.w = __byte_perm(min(y[6], 65535), min(y[7], 65535), 0x5410);
-                *reinterpret_cast<uint4*>(myy + (cb + jj) * 2) = o;
+                if constexpr (EPI == TC_EPI_RES22) *reinterpret_cast<uint4*>(yslice + tma_tile_off(RB, lane, (cb + jj) >> 3)) = o;
+                else *reinterpret_cast<uint4*>(myy + (cb + jj) * 2) = o;
               } else {
                 *reinterpret_cast<int4*>(myy + (cb + jj) * 4) = make_int4(y[0], y[1], y[2], y[3]);
                 *reinterpret_cast<int4*>(myy + (cb + jj) * 4 + 16) = make_int4(y[4], y[5], y[6], y[7]);
               }
             }
-            if (low_bits == 8) *reinterpret_cast<uint4*>(mylow + cb + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            else if (low_bits == 4) *reinterpret_cast<uint2*>(mylow + ((cb + j) >> 1)) = make_uint2(lw[0], lw[1]);
+            if constexpr (EPI == TC_EPI_RES22) {   // dense swizzled low tile (TMA box): 8-bit rows of CW bytes, 4-bit rows of CW/2 bytes
+              if (low_bits == 8) *reinterpret_cast<uint4*>(lowslice + tma_tile_off(CW, lane, (cb + j) >> 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              else if (low_bits == 4) *reinterpret_cast<uint2*>(lowslice + tma_tile_off(CW / 2, lane, (cb + j) >> 5) + (((cb + j) >> 1) & 8)) = make_uint2(lw[0], lw[1]);
+            } else {
+              if (low_bits == 8) *reinterpret_cast<uint4*>(mylow + cb + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              else if (low_bits == 4) *reinterpret_cast<uint2*>(mylow + ((cb + j) >> 1)) = make_uint2(lw[0], lw[1]);
+            }
           }
         }
       }
@@ -579,9 +604,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       if (lane == 0) mbar_arrive(tempty_bar(buf));
       if (ew == 0) trace(2, tile_iter, 3);
 
+      const int rows_ok = p.M - (m0 + quarter * 32);
+      if constexpr (EPI == TC_EPI_RES22) {
+        // TMA tile stores: every lane publishes its writes to the async proxy, one lane issues two box stores (rows past M
+        // are clipped by the tensor map); they drain while the next tile is computed
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&maps.y, c0 * 2, m0 + quarter * 32, smem_u32(yslice));
+          if (low_bits == 8) tma_store_2d(&maps.low, c0, m0 + quarter * 32, smem_u32(lowslice));
+          else if (low_bits == 4) tma_store_2d(&maps.low, c0 >> 1, m0 + quarter * 32, smem_u32(lowslice));
+          bulk_commit();
+        }
+      } else {
       // coalesced copy-out of the staged outputs: a warp instruction writes whole rows (4 rows x 128 B for uint16 tiles);
       // all shared-memory reads are issued before the first global store
-      const int rows_ok = p.M - (m0 + quarter * 32);
       if constexpr (Y_ES != 0) {
         constexpr int CPR = CW * Y_ES / 16;
         uint8_t* gy = reinterpret_cast<uint8_t*>(p.out) + ((size_t)(m0 + quarter * 32) * p.Cout + c0) * Y_ES;
@@ -623,7 +660,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         }
       }
       __syncwarp();   // staging slices are rewritten by the next tile
+      }
       if (ew == 0) trace(2, tile_iter, 4);
+    }
+    if constexpr (EPI == TC_EPI_RES22) {
+      if (lane == 0) bulk_wait_all();
     }
     if constexpr (IS_RES) {
       cp_async_wait<0>();
