@@ -62,7 +62,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -297,7 +297,7 @@ def roofline_leg(hb, ops, q, dev_pool, a):
             "traffic": None, "launches_per_step": t["launches"], "share_of_step": t["ms"] / total_ms,
             "algorithmic_bytes_per_step": t["bytes"], "avg_launch_ms": t["ms"] / t["launches"],
             "tensor_tops": 2 * t["macs"] / (t["ms"] / 1e3) / 1e12,
-            "note": "all %d %s launches of one step: sum of algorithmic bytes / sum of CUDA-event durations (eager pass)" % (t["launches"], top)}
+            "note": "all %d %s launches of one step (tcgen05 conv_tc_kernel / IMMA conv_igemm_kernel behind hawq_conv2d): sum of algorithmic bytes / sum of CUDA-event durations (eager pass on the launch stream)" % (t["launches"], top)}
     detail = {"layers": layers, "by_kernel": agg, "act_bytes": sum(g["bytes"] for g in agg.values()), "eager_step_ms": total_ms}
     return roof, detail
 

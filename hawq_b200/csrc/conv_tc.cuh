@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     if (tma_a) {
       if (tid == 0) {
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+          const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
           for (int kt = 0; kt < KT; ++kt, ++it) {
             const int stage = it % STAGES;
             mbar_wait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       }
     } else {
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
       int hi0[A_PASSES], wi0[A_PASSES], pix[A_PASSES];
       bool a_ok[A_PASSES];
 #pragma unroll
@@ -413,14 +413,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     constexpr int RB = CW * 2;                  // RES22 tile row bytes (uint16)
     auto prefetch_residual_tma = [&](int tile, uint32_t k) {      // k-th tile of this CTA -> buffer k & 1
       if (lane == 0) {
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
         mbar_arrive_expect_tx(res_bar(ew, k & 1), 32 * RB);
         tma_load_2d(smem_u32(slice0 + (k & 1) * S::SLICE), &maps.res, (n0 + half * CW) * 2, m0 + quarter * 32, res_bar(ew, k & 1));
       }
     };
     auto prefetch_residual = [&](int tile, uint8_t* dst) {
       if constexpr (IS_RES) {
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
         const uint8_t* gres = reinterpret_cast<const uint8_t*>(p.res) + ((size_t)(m0 + quarter * 32) * p.Cout + n0 + half * CW) * RES_ES;
         const int rows_ok = p.M - (m0 + quarter * 32);
 #pragma unroll
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       if ((int)blockIdx.x < num_tiles) prefetch_residual_tma(blockIdx.x, 0);
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
       const int buf = tile_iter & 1;
       const int c0 = n0 + half * CW;             // first global channel of this warp
       uint8_t* rslice = slice0 + (EPI == TC_EPI_RES22 ? (tile_iter & 1) * S::SLICE : 0);

@@ -128,14 +128,14 @@ def conv2d(x, desc, ep, w, chan, res=None, res_chan=None, fscale=None, out=None,
     ev = _begin()
     _lib.check(_lib.load().hawq_conv2d(h, C.byref(desc), C.byref(ep), _p(x), _p(w), _p(chan), _p(res), _p(res_chan),
                                        _p(fscale), _p(out), _p(out_low), s))
-    _count("conv_igemm", conv_work(desc, ep) if ev is not None else None, ev)
+    _count("hawq_conv2d", conv_work(desc, ep) if ev is not None else None, ev)
 
 
 def linear(x, w, chan, fscale, out, n, k, cout, cout_pad):
     h, s = _ctx(x)
     ev = _begin()
     _lib.check(_lib.load().hawq_linear_i8(h, n, k, cout, cout_pad, _p(x), _p(w), _p(chan), _p(fscale), _p(out), s))
-    _count("conv_igemm", (n * k * cout, n * k + cout_pad * k + 20 * cout_pad + n * cout * 4) if ev is not None else None, ev)
+    _count("hawq_linear", (n * k * cout, n * k + cout_pad * k + 20 * cout_pad + n * cout * 4) if ev is not None else None, ev)
 
 
 def stem_conv(x, w, chan, clamp, out, n, hh, ww):
