@@ -227,6 +227,7 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   p.trace = g_trace;
   p.tma_a = 0;
   p.tma_io = 0;
+  p.patch_rows = 0;
   if (ep->mode == HAWQ_EPI_RESIDUAL) {
     if (ep->res_kind == 0 && !dyadic_is_fast(ep->res_m, ep->res_e)) p.slow_scalar = 1;
     if (ep->low_bits != 0 && !dyadic_is_fast(ep->low_m, ep->low_e)) p.slow_scalar = 1;
@@ -290,6 +291,15 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
     const long long tiles = ((M + TC_BM - 1) / TC_BM) * (d->Cout / (wide ? 128 : 64));
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool patch_enabled = [] { const char* e = getenv("HAWQ_B200_PATCH"); return !(e && e[0] == '0'); }();
+    if (patch_enabled && ep->mode == HAWQ_EPI_REQUANT && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && 128 + 2 * d->W + 2 <= 256) {
+      const uint32_t rows = 128 + 2 * d->W + 2;
+      const uint32_t rowb = a4 ? 32 : 64;
+      if (make_map_2d(&maps.patch, x, (uint64_t)p.x_pix_bytes, (uint64_t)d->N * d->H * d->W, (uint64_t)p.x_pix_bytes, rowb, rows,
+                      a4 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B))
+        return fail(HAWQ_ERR_CUDA, "hawq_conv2d: cuTensorMapEncodeTiled (input patch) failed");
+      p.patch_rows = (int)rows;
+    }
     if (ep->mode == HAWQ_EPI_RESIDUAL && ep->res_kind == 0 && ep->res_bits == 16 && ep->y_bits == 16) {
       const uint32_t cw = bn / 2;   // columns per epilogue warp
       const CUtensorMapSwizzle sw_y = cw * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;

@@ -31,6 +31,7 @@ struct alignas(64) TcMaps {
   CUtensorMap res;   // uint16 residual stream [M][Cout], box (CW * 2 bytes) x 32 rows, SWIZZLE_128B
   CUtensorMap y;     // uint16 residual stream out, same shape
   CUtensorMap low;   // low-bit activation out [M][Cout * bits / 8], box (CW * bits / 8) x 32 rows
+  CUtensorMap patch; // input pixels as a matrix [N*H*W][Cin * bits / 8], box (64 | 32 bytes) x (128 + 2W + 2) rows (3x3 patch mode)
 };
 
 constexpr int TC_BM = 128;
@@ -50,7 +51,7 @@ template <int BN, int EPI, bool A4 = false>
 struct TcSmem {
   // pipeline depth: RESIDUAL epilogues are epilogue-bound and need shared memory for their tiles; the others are
   // load-latency-bound and get a deep ring.  The producer keeps LAG + 1 k-tiles in flight per thread.
-  static constexpr int STAGES = (EPI == TC_EPI_RES22) ? (A4 && BN == 128 ? 4 : 5) : (EPI >= TC_EPI_RES44) ? 5 : (EPI == TC_EPI_RAW) ? 7 : (BN == 128 ? 10 : 12);
+  static constexpr int STAGES = (EPI == TC_EPI_RES22) ? (A4 && BN == 128 ? 4 : 5) : (EPI >= TC_EPI_RES44) ? 5 : (EPI == TC_EPI_RAW) ? 7 : (BN == 128 ? 8 : 10);
   static constexpr int LAG = STAGES - 2;
   static constexpr int A_STAGE = TC_BM * 64;
   static constexpr int B_STAGE = BN * 64;
@@ -72,7 +73,9 @@ struct TcSmem {
   static constexpr int M1_OFF = CST_OFF + BN * 16;                         // double M1[BN]
   static constexpr int STG_SLOT = TC_BM * 32;                              // packed 4-bit rows of one k-tile (A4 only)
   static constexpr int STG_OFF = M1_OFF + BN * 8;
-  static constexpr int BAR_OFF = STG_OFF + (A4 ? (LAG + 1) * STG_SLOT : 0);   // mbarriers + tmem base
+  static constexpr int PATCH_BUF = (EPI == TC_EPI_REQ) ? 256 * 64 : 0;      // 3x3 patch mode: two buffers of <= 256 pixel rows
+  static constexpr int PATCH_OFF = STG_OFF + (A4 ? (LAG + 1) * STG_SLOT : 0);
+  static constexpr int BAR_OFF = PATCH_OFF + 2 * PATCH_BUF;               // mbarriers + tmem base
   static constexpr int TOTAL = BAR_OFF + 1024 + 1024;                       // + slack for 1024 B alignment of the ring
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::BAR_OFF + 8 * (2 * STAGES + 4));
   auto res_bar = [&](int ew_, int b) { return bar_base + 8u * (2 * STAGES + 6 + ew_ * 2 + b); };   // TMA residual tiles (per epilogue warp)
+  auto patch_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 22 + b); };                    // TMA input patches (3x3 patch mode)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // debug timeline: role 0 producer (warp 0), 1 MMA, 2 epilogue (first epilogue warp); 8 events x 64 tiles per role
@@ -236,13 +240,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   // ---- one-time setup ----
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), p.tma_a ? 1 : TC_PRODUCER_WARPS * 32 + 1);   // + the expect_tx arrival of the TMA-issuing thread
+      mbar_init(full_bar(s), (p.tma_a && !(EPI == TC_EPI_REQ && p.patch_rows != 0)) ? 1 : TC_PRODUCER_WARPS * 32 + 1);   // + the expect_tx arrival of the TMA-issuing thread
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), TC_EPI_WARPS);
       for (int w = 0; w < TC_EPI_WARPS; ++w) mbar_init(res_bar(w, b), 1);
+      mbar_init(patch_bar(b), 1);
     }
     fence_barrier_init();
   }
@@ -276,7 +281,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         *reinterpret_cast<uint4*>(dst + (((2 * a_ch + 1) ^ sw) << 4)) = hi;
       }
     };
-    if (tma_a) {
+    if (EPI == TC_EPI_REQ && p.patch_rows != 0) {
+      // ---- 3x3 stride-1 pad-1: im2col from shared memory.  One TMA box per (tile, Cin chunk) brings the contiguous pixel
+      // range [P0 - W - 1, P0 + 127 + W + 1] (zero-filled outside the tensor) into a patch buffer; for tap (kh, kw) output row
+      // r needs patch row r + kh*W + kw.  Each producer thread copies (and for packed 4-bit input expands) its own row into
+      // the swizzled A tile, writing zeros where the tap falls into the padding.  L2 -> SM traffic: ~1.3x instead of 9x.
+      constexpr int PROWB = A4 ? 32 : 64;                  // bytes per patch row
+      const int row = tid;
+      const uint32_t a_sw = (row >> 1) & 3;
+      const int chunks = p.cin_chunks;
+      const uint32_t patch_bytes = (uint32_t)p.patch_rows * PROWB;
+      const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const long long total_g = (long long)my_tiles * chunks;           // (tile, chunk) pairs of this CTA
+      auto issue_patch = [&](long long g) {                              // thread 0 only
+        const int tile = blockIdx.x + (int)(g / chunks) * gridDim.x;
+        const int c = (int)(g % chunks);
+        const int m0 = (tile % m_tiles) * BM;
+        mbar_arrive_expect_tx(patch_bar((int)(g & 1)), patch_bytes);
+        tma_load_2d(smem_base + S::PATCH_OFF + (uint32_t)(g & 1) * S::PATCH_BUF, &maps.patch, c * PROWB, m0 - p.W - 1, patch_bar((int)(g & 1)));
+      };
+      if (tid == 0 && total_g > 0) issue_patch(0);
+      long long g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+        const int m = m0 + row;
+        const bool row_ok = m < p.M;
+        const int mm = row_ok ? m : 0;
+        const int rr = mm % (p.H * p.W);
+        const int h = rr / p.W, w = rr - h * p.W;
+        for (int c = 0; c < chunks; ++c, ++g) {
+          if (tid == 0 && g + 1 < total_g) issue_patch(g + 1);            // prefetch into the buffer freed one chunk ago
+          mbar_wait(patch_bar((int)(g & 1)), (uint32_t)((g >> 1) & 1));
+          const uint8_t* patch = smem + S::PATCH_OFF + (g & 1) * S::PATCH_BUF;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap, ++it) {
+            const int kh = tap / 3, kw = tap - kh * 3;
+            const int stage = it % STAGES;
+            mbar_wait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
+            if (tid == 0) {                                              // weights of this k-tile: K index = tap * Cin + c * 64
+              mbar_arrive_expect_tx(full_bar(stage), S::B_STAGE);
+              tma_load_2d(smem_base + stage * S::STAGE + S::A_STAGE, &maps.b, (tap * chunks + c) * 64, n0, full_bar(stage));
+            }
+            const bool v = row_ok && (unsigned)(h + kh - 1) < (unsigned)p.H && (unsigned)(w + kw - 1) < (unsigned)p.W;
+            const int pr = row + kh * p.W + kw;
+            uint8_t* dst = smem + stage * S::STAGE + row * 64;
+            if constexpr (!A4) {
+              const uint32_t p_sw = (pr >> 1) & 3;
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch) {
+                uint4 val = make_uint4(0, 0, 0, 0);
+                if (v) val = *reinterpret_cast<const uint4*>(patch + pr * 64 + ((ch ^ p_sw) << 4));
+                *reinterpret_cast<uint4*>(dst + ((ch ^ a_sw) << 4)) = val;
+              }
+            } else {
+              const uint32_t p_sw = (pr >> 2) & 1;                       // SWIZZLE_32B rows
+#pragma unroll
+              for (int blk = 0; blk < 2; ++blk) {
+                uint4 wv = make_uint4(0, 0, 0, 0);
+                if (v) wv = *reinterpret_cast<const uint4*>(patch + pr * 32 + ((blk ^ p_sw) << 4));
+                const uint4 lo = make_uint4(wv.x & 0x0F0F0F0Fu, wv.y & 0x0F0F0F0Fu, wv.z & 0x0F0F0F0Fu, wv.w & 0x0F0F0F0Fu);
+                const uint4 hi = make_uint4((wv.x >> 4) & 0x0F0F0F0Fu, (wv.y >> 4) & 0x0F0F0F0Fu, (wv.z >> 4) & 0x0F0F0F0Fu, (wv.w >> 4) & 0x0F0F0F0Fu);
+                *reinterpret_cast<uint4*>(dst + (((2 * blk) ^ a_sw) << 4)) = lo;
+                *reinterpret_cast<uint4*>(dst + (((2 * blk + 1) ^ a_sw) << 4)) = hi;
+              }
+            }
+            fence_proxy_async();
+            mbar_arrive(full_bar(stage));
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(TC_PRODUCER_WARPS * 32));   // every thread is done reading this patch buffer
+        }
+      }
+    } else if (tma_a) {
       if (tid == 0) {
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
           const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
