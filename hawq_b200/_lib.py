@@ -27,7 +27,7 @@ class hawq_chan(C.Structure):
 
 
 class hawq_conv_desc(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("N", "H", "W", "Cin", "Cout", "kh", "kw", "stride", "pad", "a_bits")]
+    _fields_ = [(n, C.c_int32) for n in ("N", "H", "W", "Cin", "Cout", "kh", "kw", "stride", "pad", "a_bits", "w_layout")]
 
 
 class hawq_epilogue_desc(C.Structure):
@@ -74,6 +74,7 @@ SIGNATURES = {
     "hawq_dyadic": (_i32, [C.c_double, C.POINTER(_u32), C.POINTER(_i32)]),
     "hawq_rhe_requant_host": (_i64, [_i32, _u32, _i32]),
     "hawq_permute_weights_for_i4": (_i32, [_vp, _i64, _i32]),
+    "hawq_retile_weights": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "hawq_debug_set_trace": (_i32, [_vp]),
     "hawq_workspace_bytes": (_i64, [C.POINTER(hawq_conv_desc), C.POINTER(hawq_epilogue_desc)]),
 }

@@ -228,6 +228,7 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   p.tma_a = 0;
   p.tma_io = 0;
   p.patch_rows = 0;
+  p.w_tiled = nullptr;
   if (ep->mode == HAWQ_EPI_RESIDUAL) {
     if (ep->res_kind == 0 && !dyadic_is_fast(ep->res_m, ep->res_e)) p.slow_scalar = 1;
     if (ep->low_bits != 0 && !dyadic_is_fast(ep->low_m, ep->low_e)) p.slow_scalar = 1;
@@ -282,7 +283,8 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
     const int bn = (d->Cout % 128 == 0) ? 128 : 64;
     TcMaps maps;
     memset(&maps, 0, sizeof(maps));
-    if (make_map_2d(&maps.b, w, (uint64_t)p.K, (uint64_t)d->Cout, (uint64_t)p.K, 64, (uint32_t)bn, CU_TENSOR_MAP_SWIZZLE_64B))
+    if (d->w_layout == 1) p.w_tiled = w + (size_t)d->Cout * p.K;     // caller appended the re-tiled copy (hawq_retile_weights)
+    else if (make_map_2d(&maps.b, w, (uint64_t)p.K, (uint64_t)d->Cout, (uint64_t)p.K, 64, (uint32_t)bn, CU_TENSOR_MAP_SWIZZLE_64B))
       return fail(HAWQ_ERR_CUDA, "hawq_conv2d: cuTensorMapEncodeTiled (weights) failed");
     p.tma_a = (!a4 && d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0) ? 1 : 0;
     if (p.tma_a && make_map_2d(&maps.a, x, (uint64_t)d->Cin, (uint64_t)M, (uint64_t)d->Cin, 64, TC_BM, CU_TENSOR_MAP_SWIZZLE_64B))
@@ -499,6 +501,15 @@ int hawq_permute_weights_for_i4(int8_t* host_w, int64_t rows_times_taps, int32_t
 }
 
 int64_t hawq_workspace_bytes(const hawq_conv_desc*, const hawq_epilogue_desc*) { return 0; }
+
+int hawq_retile_weights(hawq_handle* h, const int8_t* w_ohwi, int32_t Cout, int64_t K, int8_t* out, void* stream) {
+  if (!h || !w_ohwi || !out) return fail(HAWQ_ERR_BAD_ARG, "hawq_retile_weights: null argument");
+  if (Cout % 64 != 0 || K % 64 != 0) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_retile_weights: Cout and K must be multiples of 64");
+  const int bn = (Cout % 128 == 0) ? 128 : 64;
+  const long long chunks = (long long)Cout * K / 16;
+  retile_weights_kernel<<<grid_for(chunks, h->sm_count), 256, 0, (cudaStream_t)stream>>>(w_ohwi, Cout, (int)K, bn, out);
+  return launch_check("retile_weights");
+}
 
 int hawq_debug_set_trace(int64_t* device_buffer) {
   g_trace = reinterpret_cast<long long*>(device_buffer);

@@ -42,6 +42,7 @@ struct ConvParams {
   int slow_scalar;   // host-checked: a scalar dyadic pair (res / low) has ratio > 1 -> generic 64-bit requant
   int tma_a;         // tcgen05 kernel: activations are fetched by TMA (1x1 stride-1 int8 layers)
   int tma_io;        // tcgen05 kernel: uint16 residual tile in / outputs out through TMA
+  const int8_t* w_tiled;  // tcgen05 kernel: weights re-tiled into contiguous pre-swizzled [n_tile][k_tile][BN][64] blocks
   int patch_rows;    // tcgen05 kernel, 3x3 stride-1 pad-1 layers: rows of the shared-memory input patch (128 + 2W + 2), 0 = gather mode
   long long* trace;  // debug timeline (hawq_debug_set_trace): [role][tile][event] clock64 values of CTA 0, or null
 };

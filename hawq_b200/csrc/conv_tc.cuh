@@ -116,6 +116,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// 1-D bulk copy global -> shared (contiguous bytes, multiple of 16), completion (bytes) on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
 // TMA: 2-D tiled box shared -> global (bulk async group)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t smem_src) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
@@ -320,7 +325,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
             mbar_wait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
             if (tid == 0) {                                              // weights of this k-tile: K index = tap * Cin + c * 64
               mbar_arrive_expect_tx(full_bar(stage), S::B_STAGE);
-              tma_load_2d(smem_base + stage * S::STAGE + S::A_STAGE, &maps.b, (tap * chunks + c) * 64, n0, full_bar(stage));
+              if (p.w_tiled) bulk_load_1d(smem_base + stage * S::STAGE + S::A_STAGE, p.w_tiled + ((size_t)(n0 / BN) * KT + (tap * chunks + c)) * S::B_STAGE, S::B_STAGE, full_bar(stage));
+              else tma_load_2d(smem_base + stage * S::STAGE + S::A_STAGE, &maps.b, (tap * chunks + c) * 64, n0, full_bar(stage));
             }
             const bool v = row_ok && (unsigned)(h + kh - 1) < (unsigned)p.H && (unsigned)(w + kw - 1) < (unsigned)p.W;
             const int pr = row + kh * p.W + kw;
@@ -361,7 +367,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
             const uint32_t a_base = smem_base + stage * S::STAGE;
             mbar_arrive_expect_tx(full_bar(stage), S::A_STAGE + S::B_STAGE);
             tma_load_2d(a_base, &maps.a, kt * 64, m0, full_bar(stage));
-            tma_load_2d(a_base + S::A_STAGE, &maps.b, kt * 64, n0, full_bar(stage));
+            if (p.w_tiled) bulk_load_1d(a_base + S::A_STAGE, p.w_tiled + ((size_t)(n0 / BN) * KT + kt) * S::B_STAGE, S::B_STAGE, full_bar(stage));
+            else tma_load_2d(a_base + S::A_STAGE, &maps.b, kt * 64, n0, full_bar(stage));
           }
         }
       }
@@ -402,7 +409,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         }
         if (tid == 0) {                         // weights: one TMA box (64 x BN, SWIZZLE_64B) per k-tile
           mbar_arrive_expect_tx(full_bar(stage), S::B_STAGE);
-          tma_load_2d(b_base, &maps.b, kt * 64, n0, full_bar(stage));
+          if (p.w_tiled) bulk_load_1d(b_base, p.w_tiled + ((size_t)(n0 / BN) * KT + kt) * S::B_STAGE, S::B_STAGE, full_bar(stage));
+          else tma_load_2d(b_base, &maps.b, kt * 64, n0, full_bar(stage));
         }
         if constexpr (!A4) {
           // int8 rows need no post-processing: the barrier is signalled by the copy hardware itself, the producer never
@@ -755,6 +763,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   if (warp == TC_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// One-time re-tiling of OHWI int8 weights for the tcgen05 kernel: block (n_tile, k_tile) = BN rows x 64 bytes, stored
+// contiguously with the SWIZZLE_64B pattern already applied, so a k-tile of B is one linear bulk copy.
+__global__ void __launch_bounds__(256) retile_weights_kernel(const int8_t* __restrict__ w, int Cout, int K, int BN, int8_t* __restrict__ out) {
+  const int kt_total = K / 64;
+  const long long chunks = (long long)Cout * K / 16;
+  for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < chunks; id += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(id & 3);
+    const long long rk = id >> 2;                 // (row, k-tile)
+    const int kt = (int)(rk % kt_total);
+    const int row = (int)(rk / kt_total);
+    const int nt = row / BN, r = row % BN;
+    const int4 v = *reinterpret_cast<const int4*>(w + (size_t)row * K + kt * 64 + c * 16);
+    *reinterpret_cast<int4*>(out + ((size_t)nt * kt_total + kt) * BN * 64 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4)) = v;
   }
 }
 

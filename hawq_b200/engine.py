@@ -116,6 +116,54 @@ class CompiledModel:
             out = self._run(32)
         return out
 
+    def run_pipelined(self, host_batches, post=None):
+        """Exact forward over an iterable of pinned host batches with copy/compute overlap: the H2D copy of batch i+1 runs on a
+        copy stream while batch i computes; logits and the status flags come back through pinned buffers and are checked one
+        step later (a raised overflow flag re-runs that batch through ``__call__``, i.e. the exact int32 / saturating graphs).
+        ``post`` (e.g. ``all_gather_logits``) is applied to the device logits before they are read back.
+        Yields the host logits tensor of every batch, in order (valid until the second next iteration)."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_pipe"):
+            cs = torch.cuda.Stream(device=dev)
+            out = self.outs[self.residual_bits]
+            if post is not None:
+                out = post(out)
+            self._pipe = dict(copy=cs, stage=[torch.empty_like(self.static_in) for _ in range(2)],
+                              out=[torch.empty(out.shape, dtype=out.dtype).pin_memory() for _ in range(2)],
+                              flag=[torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)],
+                              h2d=[torch.cuda.Event() for _ in range(2)], free=[torch.cuda.Event() for _ in range(2)],
+                              done=[torch.cuda.Event() for _ in range(2)])
+        P = self._pipe
+        prev = None
+
+        def finish(slot, xb):
+            P["done"][slot].synchronize()
+            if int(P["flag"][slot][0]) & 7:
+                return self(xb).to("cpu")          # rare: exact fallback path, synchronous
+            return P["out"][slot]
+
+        for i, xb in enumerate(host_batches):
+            slot = i & 1
+            with torch.cuda.stream(P["copy"]):
+                P["copy"].wait_event(P["free"][slot])
+                P["stage"][slot].copy_(xb, non_blocking=True)
+                P["h2d"][slot].record(P["copy"])
+            main.wait_event(P["h2d"][slot])
+            self.static_in.copy_(P["stage"][slot], non_blocking=True)
+            P["free"][slot].record(main)
+            out = self._run(self.residual_bits)
+            if post is not None:
+                out = post(out)
+            P["out"][slot].copy_(out, non_blocking=True)
+            P["flag"][slot].copy_(self.flag, non_blocking=True)
+            P["done"][slot].record(main)
+            if prev is not None:
+                yield finish(*prev)
+            prev = (slot, xb)
+        if prev is not None:
+            yield finish(*prev)
+
     @property
     def gpu_launches(self):
         return self.launches.get(self.residual_bits, 0)

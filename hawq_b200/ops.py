@@ -91,8 +91,20 @@ def make_chan(bias, m, e):
     return torch.from_numpy(a)
 
 
-def conv_desc(N, H, W, Cin, Cout, kh, kw, stride, pad, a_bits):
-    return hawq_conv_desc(N, H, W, Cin, Cout, kh, kw, stride, pad, a_bits)
+def conv_desc(N, H, W, Cin, Cout, kh, kw, stride, pad, a_bits, w_layout=0):
+    return hawq_conv_desc(N, H, W, Cin, Cout, kh, kw, stride, pad, a_bits, w_layout)
+
+
+def upload_weights(w_ohwi_cpu, device):
+    """int8 OHWI host weights -> device buffer [OHWI | tcgen05 re-tiled copy] (hawq_conv_desc.w_layout = 1)."""
+    cout = w_ohwi_cpu.shape[0]
+    k = w_ohwi_cpu.numel() // cout
+    buf = torch.empty(2 * cout * k, dtype=torch.int8, device=device)
+    buf[:cout * k].copy_(w_ohwi_cpu.reshape(-1))
+    idx = buf.device.index if buf.device.index is not None else torch.cuda.current_device()
+    _lib.check(_lib.load().hawq_retile_weights(handle(idx), C.c_void_p(buf.data_ptr()), cout, k, C.c_void_p(buf.data_ptr() + cout * k),
+                                               C.c_void_p(torch.cuda.current_stream(idx).cuda_stream)))
+    return buf
 
 
 def epilogue(mode, relu=0, out_bits=0, clamp=(0, 0), res_kind=0, res_bits=0, res_me=(0, 1), y_bits=0, low_bits=0,

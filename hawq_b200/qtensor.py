@@ -207,7 +207,8 @@ def _conv_cache(mod, a_sf, a_bits, device):
                 raise NotImplementedError("hawq_b200 convolutions need Cin and Cout multiples of 64 (got %d, %d)" % (cin, cout))
             if a_bits == 4:
                 ops.permute_weights_for_i4(w)
-        ent = dict(w=w.to(device), w_sf=w_sf, bias=bias, cout=cout, cin=cin, k=kh, stride=conv.stride[0],
+        tiled = (not stem) and torch.device(device).type == "cuda"
+        ent = dict(w=ops.upload_weights(w, device) if tiled else w.to(device), w_layout=1 if tiled else 0, w_sf=w_sf, bias=bias, cout=cout, cin=cin, k=kh, stride=conv.stride[0],
                    pad=conv.padding[0], stem=stem, chan={})
     c[key] = ent
     return ent
@@ -286,7 +287,7 @@ def _conv_out_hw(n, ent):
 
 def _launch_conv(n, ent, ep, chan, device, out=None, out_low=None, res=None, res_chan=None):
     nb, hh, ww, _, _ = _conv_out_hw(n, ent)
-    d = ops.conv_desc(nb, hh, ww, ent["cin"], ent["cout"], ent["k"], ent["k"], ent["stride"], ent["pad"], n.src.bits)
+    d = ops.conv_desc(nb, hh, ww, ent["cin"], ent["cout"], ent["k"], ent["k"], ent["stride"], ent["pad"], n.src.bits, ent["w_layout"])
     ops.conv2d(n.src.data, d, ep, ent["w"], chan, res=res, res_chan=res_chan, out=out, out_low=out_low)
 
 

@@ -65,6 +65,7 @@ typedef struct {
   int32_t N, H, W, Cin, Cout;
   int32_t kh, kw, stride, pad;
   int32_t a_bits;    /* 8: int8 NHWC input; 4: packed unsigned nibbles (hawq nibble order) */
+  int32_t w_layout;  /* 0: w = OHWI only; 1: w = OHWI followed by the hawq_retile_weights copy (2 * Cout * K bytes) */
 } hawq_conv_desc;
 
 enum hawq_epilogue_mode {
@@ -187,6 +188,11 @@ int hawq_dyadic(double ratio, uint32_t* m, int32_t* e);
 int64_t hawq_rhe_requant_host(int32_t v, uint32_t m, int32_t e);
 /* K permutation inside each 32-channel block for layers whose input is packed 4-bit (in place, int8 OHWI, host memory) */
 int hawq_permute_weights_for_i4(int8_t* host_w, int64_t rows_times_taps, int32_t Cin);
+/* Re-tile int8 OHWI weights [Cout][K] for the tcgen05 convolution: block (n_tile, k_tile) = BN rows x 64 bytes (BN = 128 when
+ * Cout % 128 == 0, else 64), stored contiguously with the shared-memory swizzle pre-applied, so the kernel fetches a k-tile of
+ * weights with one linear bulk copy.  `out` (Cout * K bytes) is normally w_ohwi + Cout * K, i.e. the copy is appended to the OHWI
+ * tensor and announced with hawq_conv_desc.w_layout = 1.  Device pointers, asynchronous on the stream. */
+int hawq_retile_weights(hawq_handle* h, const int8_t* w_ohwi, int32_t Cout, int64_t K, int8_t* out, void* stream);
 /* debug: device int64[3][64][8] receiving clock64 timelines (producer / MMA / epilogue roles of CTA 0, first 64 tiles) of
  * subsequent tcgen05 convolution launches; null switches tracing off.  Not for production use. */
 int hawq_debug_set_trace(int64_t* device_buffer);

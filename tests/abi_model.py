@@ -87,7 +87,7 @@ status = {"flags": 0}
 def conv2d(x, desc, ep, w, chan, res=None, res_chan=None, fscale=None, out=None, out_low=None):
     n, h, wd, cin, cout = desc.N, desc.H, desc.W, desc.Cin, desc.Cout
     xa = decode(x, desc.a_bits, desc.a_bits == 8).reshape(n, h, wd, cin)
-    wa = w.detach().cpu().numpy().astype(I64).reshape(cout, desc.kh, desc.kw, cin)
+    wa = w.detach().cpu().numpy().astype(I64).reshape(-1)[:cout * desc.kh * desc.kw * cin].reshape(cout, desc.kh, desc.kw, cin)
     if desc.a_bits == 4:
         wa = unpermute_i4_weights(wa)
     acc = ir.conv2d_nhwc(xa, wa, desc.stride, desc.pad)

@@ -38,9 +38,10 @@ def out_buf(numel, bits):
     return torch.zeros(numel // 2 if bits == 4 else numel, dtype=dt)
 
 
-def run_both(fn_name, cpu_args, out_keys):
+def run_both(fn_name, cpu_args, out_keys, gpu_overrides=None):
     """cpu_args: dict of kwargs with CPU tensors; out_keys: names of output tensors.  Returns (cpu_outs, gpu_outs)."""
     gpu_args = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in cpu_args.items()}
+    gpu_args.update(gpu_overrides or {})
     getattr(am, fn_name)(**cpu_args)
     getattr(ops, fn_name)(**gpu_args)
     torch.cuda.synchronize()
@@ -78,7 +79,10 @@ def test_conv_requant(geom, a_bits, tc):
         chan = make_chan(r, cout, ratio_lo=1e-5 if out_bits <= 8 else 1e-3)
         d = ops.conv_desc(n, h, w, cin, cout, k, k, s, p, a_bits)
         ep = ops.epilogue(EPI_REQUANT, relu=relu, out_bits=out_bits, clamp=clamp, flags=TC_FLAG * tc)
-        (c_out,), (g_out,) = run_both("conv2d", dict(x=x, desc=d, ep=ep, w=wt, chan=chan, out=out_buf(n * ho * wo * cout, out_bits)), ["out"])
+        over = None
+        if tc and DEV != "cpu" and (n + h) % 2 == 0:   # half of the geometries: weights re-tiled for linear bulk loads (w_layout = 1)
+            over = dict(w=ops.upload_weights(wt, DEV), desc=ops.conv_desc(n, h, w, cin, cout, k, k, s, p, a_bits, 1))
+        (c_out,), (g_out,) = run_both("conv2d", dict(x=x, desc=d, ep=ep, w=wt, chan=chan, out=out_buf(n * ho * wo * cout, out_bits)), ["out"], over)
         assert torch.equal(c_out, g_out), (geom, a_bits, out_bits, tc)
 
 
