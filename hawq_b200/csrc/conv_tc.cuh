@@ -319,40 +319,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
           mbar_wait(patch_bar((int)(g & 1)), (uint32_t)((g >> 1) & 1));
           const uint8_t* patch = smem + S::PATCH_OFF + (g & 1) * S::PATCH_BUF;
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap, ++it) {
-            const int kh = tap / 3, kw = tap - kh * 3;
-            const int stage = it % STAGES;
-            mbar_wait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
-            if (tid == 0) {                                              // weights of this k-tile: K index = tap * Cin + c * 64
-              mbar_arrive_expect_tx(full_bar(stage), S::B_STAGE);
-              if (p.w_tiled) bulk_load_1d(smem_base + stage * S::STAGE + S::A_STAGE, p.w_tiled + ((size_t)(n0 / BN) * KT + (tap * chunks + c)) * S::B_STAGE, S::B_STAGE, full_bar(stage));
-              else tma_load_2d(smem_base + stage * S::STAGE + S::A_STAGE, &maps.b, (tap * chunks + c) * 64, n0, full_bar(stage));
-            }
-            const bool v = row_ok && (unsigned)(h + kh - 1) < (unsigned)p.H && (unsigned)(w + kw - 1) < (unsigned)p.W;
-            const int pr = row + kh * p.W + kw;
-            uint8_t* dst = smem + stage * S::STAGE + row * 64;
-            if constexpr (!A4) {
-              const uint32_t p_sw = (pr >> 1) & 3;
+          for (int kh = 0; kh < 3; ++kh, it += 3) {
+            // one kernel row (kw = 0, 1, 2) per iteration: three k-tiles share the barrier waits' latency, one proxy fence
+            const bool vh = row_ok && (unsigned)(h + kh - 1) < (unsigned)p.H;
 #pragma unroll
-              for (int ch = 0; ch < 4; ++ch) {
-                uint4 val = make_uint4(0, 0, 0, 0);
-                if (v) val = *reinterpret_cast<const uint4*>(patch + pr * 64 + ((ch ^ p_sw) << 4));
-                *reinterpret_cast<uint4*>(dst + ((ch ^ a_sw) << 4)) = val;
+            for (int kw = 0; kw < 3; ++kw) {
+              const int stage = (it + kw) % STAGES;
+              mbar_wait(empty_bar(stage), (((it + kw) / STAGES) & 1) ^ 1);
+              if (tid == 0) {                                            // weights of this k-tile: K index = tap * Cin + c * 64
+                const int ktile = (kh * 3 + kw) * chunks + c;
+                mbar_arrive_expect_tx(full_bar(stage), S::B_STAGE);
+                if (p.w_tiled) bulk_load_1d(smem_base + stage * S::STAGE + S::A_STAGE, p.w_tiled + ((size_t)(n0 / BN) * KT + ktile) * S::B_STAGE, S::B_STAGE, full_bar(stage));
+                else tma_load_2d(smem_base + stage * S::STAGE + S::A_STAGE, &maps.b, ktile * 64, n0, full_bar(stage));
               }
-            } else {
-              const uint32_t p_sw = (pr >> 2) & 1;                       // SWIZZLE_32B rows
+            }
+            constexpr int NV = A4 ? 2 : 4;                               // 16-byte vectors per patch row
+            uint4 val[3][NV];
 #pragma unroll
-              for (int blk = 0; blk < 2; ++blk) {
-                uint4 wv = make_uint4(0, 0, 0, 0);
-                if (v) wv = *reinterpret_cast<const uint4*>(patch + pr * 32 + ((blk ^ p_sw) << 4));
-                const uint4 lo = make_uint4(wv.x & 0x0F0F0F0Fu, wv.y & 0x0F0F0F0Fu, wv.z & 0x0F0F0F0Fu, wv.w & 0x0F0F0F0Fu);
-                const uint4 hi = make_uint4((wv.x >> 4) & 0x0F0F0F0Fu, (wv.y >> 4) & 0x0F0F0F0Fu, (wv.z >> 4) & 0x0F0F0F0Fu, (wv.w >> 4) & 0x0F0F0F0Fu);
-                *reinterpret_cast<uint4*>(dst + (((2 * blk) ^ a_sw) << 4)) = lo;
-                *reinterpret_cast<uint4*>(dst + (((2 * blk + 1) ^ a_sw) << 4)) = hi;
+            for (int kw = 0; kw < 3; ++kw) {
+              const bool v = vh && (unsigned)(w + kw - 1) < (unsigned)p.W;
+              const int pr = row + kh * p.W + kw;
+              const uint32_t p_sw = A4 ? ((pr >> 2) & 1) : ((pr >> 1) & 3);
+#pragma unroll
+              for (int ch = 0; ch < NV; ++ch) {
+                val[kw][ch] = make_uint4(0, 0, 0, 0);
+                if (v) val[kw][ch] = *reinterpret_cast<const uint4*>(patch + pr * PROWB + ((ch ^ p_sw) << 4));
+              }
+            }
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              uint8_t* dst = smem + ((it + kw) % STAGES) * S::STAGE + row * 64;
+              if constexpr (!A4) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(dst + ((ch ^ a_sw) << 4)) = val[kw][ch];
+              } else {
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                  const uint4 wv = val[kw][blk];
+                  const uint4 lo = make_uint4(wv.x & 0x0F0F0F0Fu, wv.y & 0x0F0F0F0Fu, wv.z & 0x0F0F0F0Fu, wv.w & 0x0F0F0F0Fu);
+                  const uint4 hi = make_uint4((wv.x >> 4) & 0x0F0F0F0Fu, (wv.y >> 4) & 0x0F0F0F0Fu, (wv.z >> 4) & 0x0F0F0F0Fu, (wv.w >> 4) & 0x0F0F0F0Fu);
+                  *reinterpret_cast<uint4*>(dst + (((2 * blk) ^ a_sw) << 4)) = lo;
+                  *reinterpret_cast<uint4*>(dst + (((2 * blk + 1) ^ a_sw) << 4)) = hi;
+                }
               }
             }
             fence_proxy_async();
-            mbar_arrive(full_bar(stage));
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) mbar_arrive(full_bar((it + kw) % STAGES));
           }
           asm volatile("bar.sync 2, %0;" ::"n"(TC_PRODUCER_WARPS * 32));   // every thread is done reading this patch buffer
         }

@@ -23,12 +23,12 @@ lib = _lib.load()
 r = np.random.RandomState(0)
 for name, H, cin, cout, k, s, mode in LAYERS:
     x = torch.from_numpy(r.randint(-128, 128, size=B * H * H * cin).astype(np.int8)).to(dev)
-    w = torch.from_numpy(r.randint(-128, 128, size=(cout, k, k, cin)).astype(np.int8)).to(dev)
+    w = ops.upload_weights(torch.from_numpy(r.randint(-128, 128, size=(cout, k, k, cin)).astype(np.int8)), dev)
     me = [dyadic(1e-3)] * cout
     chan = ops.make_chan([0] * cout, [m for m, _ in me], [e for _, e in me]).to(dev)
     Ho = (H + 2 * (k // 2) - k) // s + 1
     numel = B * Ho * Ho * cout
-    d = ops.conv_desc(B, H, H, cin, cout, k, k, s, k // 2, 8)
+    d = ops.conv_desc(B, H, H, cin, cout, k, k, s, k // 2, 8, 1)
     if mode == "req":
         ep = ops.epilogue(EPI_REQUANT, relu=1, out_bits=8, clamp=(-128, 127), flags=1)
         args = dict(out=torch.zeros(numel, dtype=torch.int8, device=dev))
