@@ -97,44 +97,78 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_forward_rate(arch, scheme, batch, steps, warmup):
-    """The reference's fake-quant forward (oracle/fakequant.py restatement, pinned bit-exact to the unmodified
-    reference) on all host cores."""
+def usable_cpus(cap=32):
+    """Threads the CPU legs may use: scheduler affinity, limited by the cgroup CPU quota (os.cpu_count() reports the host's
+    cores inside a container and oversubscribing them makes oneDNN crawl), capped at `cap` (the fp32 convs do not scale further)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path, parse in (("/sys/fs/cgroup/cpu.max", lambda t: None if t.split()[0] == "max" else float(t.split()[0]) / float(t.split()[1])),
+                        ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", None)):
+        try:
+            txt = open(path).read().strip()
+            if parse is not None:
+                q = parse(txt)
+            else:
+                quota = float(txt)
+                period = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read().strip())
+                q = quota / period if quota > 0 else None
+            if q:
+                n = min(n, max(1, int(q)))
+            break
+        except (OSError, ValueError, IndexError, ZeroDivisionError):
+            continue
+    return max(1, min(n, cap))
+
+
+def cpu_forward_rate(arch, scheme, max_batch, steps, warmup, budget_s=25.0):
+    """The reference's fake-quant forward (oracle/fakequant.py restatement, pinned bit-exact to the unmodified reference)
+    on the usable host cores.  The per-step sample (images per forward) is sized from a 1-image probe so that `steps` timed
+    forwards fit in about `budget_s` seconds.  Returns (images/s, threads, seconds per step, images per step)."""
     from oracle import fakequant as fq
     from hawq_b200.bit_config import get_bit_config
     from hawq_b200.synthetic import synthetic_batch, synthetic_float_resnet
-    threads = os.cpu_count() or 1
+    threads = usable_cpus()
     torch.set_num_threads(threads)
     net = synthetic_float_resnet(arch, 0)
     m = fq.FakeQuantResNet(arch, net, get_bit_config(arch, scheme))
-    m(synthetic_batch(4, 0))
+    m(synthetic_batch(1, 0))                       # calibration (ranges do not change the amount of work)
     m.freeze()
+    x1 = synthetic_batch(1, 1)
+    m(x1)                                          # warm-up (allocator, oneDNN primitive cache)
+    t0 = time.perf_counter()
+    m(x1)
+    per_img = time.perf_counter() - t0
+    steps = max(1, min(steps, int(4 * budget_s / max(per_img, 1e-6))))   # a pathologically slow host: fewer steps rather than minutes
+    batch = int(max(1, min(max_batch, budget_s / max(steps, 1) / max(per_img, 1e-6))))
     x = synthetic_batch(batch, 1)
-    for _ in range(warmup):
+    for _ in range(min(warmup, 1)):
         m(x)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
         m(x)
         ts.append(time.perf_counter() - t0)
-    return batch / (sum(ts) / len(ts)), threads, sum(ts) / len(ts)
+    sec = sum(ts) / len(ts)
+    return batch / sec, threads, sec, batch, steps
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(a.steps, 10))
-    warm = max(1, min(a.warmup, 2))
-    ips, threads, sec = cpu_forward_rate(a.arch, a.scheme, a.cpu_batch, steps, warm)
+    steps = max(1, a.steps)
+    warm = max(1, a.warmup)
+    ips, threads, sec, cpu_b, steps = cpu_forward_rate(a.arch, a.scheme, a.cpu_batch, steps, warm, budget_s=60.0)
     line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": a.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32 emulating int8/int4 (reference fake-quant)", "data": "synthetic", "impl": "reference",
             "config": {"workload": "%s_%s_b%d" % (a.arch, a.scheme, a.batch), "arch": a.arch, "bit_config": a.scheme,
                        "batch_per_gpu": a.batch, "input": "synthetic 224x224"},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                             "sample": "%d steps of a %d-image batch through oracle/fakequant.py (torch CPU restatement of the "
-                                       "reference forward, bit-exact vs the unmodified reference in the build container)" % (steps, a.cpu_batch)},
+                             "sample": "%d steps, each the forward of %d image(s) of the workload, through oracle/fakequant.py (torch CPU restatement of the "
+                                       "reference forward, bit-exact vs the unmodified reference in the build container)" % (steps, cpu_b)},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -153,6 +187,7 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.set_num_threads(usable_cpus())            # CPU-side calibration / plan building
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -226,10 +261,10 @@ def run_ours(a):
         roof, detail = roofline_leg(hb, ops, q, dev_pool, a)
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
-        ips, threads, sec = cpu_forward_rate(a.arch, a.scheme, a.cpu_batch, 3, 1)
+        ips, threads, sec, cpu_b, _ = cpu_forward_rate(a.arch, a.scheme, a.cpu_batch, 3, 1, budget_s=20.0)
         cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": "3 forwards of a %d-image batch (%.2f s each) through oracle/fakequant.py, the torch-CPU restatement of the "
-                         "reference's fake-quant forward (the Python reference itself cannot travel to the GPU box)" % (a.cpu_batch, sec)}
+               "sample": "3 forwards of %d image(s) (%.2f s each) through oracle/fakequant.py, the torch-CPU restatement of the "
+                         "reference's fake-quant forward (the Python reference itself cannot travel to the GPU box)" % (cpu_b, sec)}
     if rank == 0:
         total_imgs = B * world * a.steps
         value = total_imgs / (ms / 1e3)

@@ -322,6 +322,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
           for (int kh = 0; kh < 3; ++kh, it += 3) {
             // one kernel row (kw = 0, 1, 2) per iteration: three k-tiles share the barrier waits' latency, one proxy fence
             const bool vh = row_ok && (unsigned)(h + kh - 1) < (unsigned)p.H;
+            const uint32_t ptile = (tile - blockIdx.x) / gridDim.x;
+            const bool tr = (warp == 0 && kh == 1 && c == 0);
+            if (tr) trace(0, ptile, 0);
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
               const int stage = (it + kw) % STAGES;
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
                 else tma_load_2d(smem_base + stage * S::STAGE + S::A_STAGE, &maps.b, ktile * 64, n0, full_bar(stage));
               }
             }
+            if (tr) trace(0, ptile, 1);
             constexpr int NV = A4 ? 2 : 4;                               // 16-byte vectors per patch row
             uint4 val[3][NV];
 #pragma unroll
@@ -363,9 +367,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
                 }
               }
             }
+            if (tr) trace(0, ptile, 2);
             fence_proxy_async();
+            if (tr) trace(0, ptile, 3);
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) mbar_arrive(full_bar((it + kw) % STAGES));
+            if (tr) trace(0, ptile, 4);
           }
           asm volatile("bar.sync 2, %0;" ::"n"(TC_PRODUCER_WARPS * 32));   // every thread is done reading this patch buffer
         }

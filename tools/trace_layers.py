@@ -59,6 +59,8 @@ for name, H, cin, cout, k, s, mode in LAYERS:
     n = min(10, int((t[2, :, 1] > 0).sum()))
     for i in range(2, n):
         p_, m_, e_ = t[0, i], t[1, i], t[2, i]
+        if k == 3:
+            print("  tile %2d | patch producer (kh=1 row of 3 taps): empty-waits %5d  lds+sts %5d  fence %5d  arrives %5d" % (i, p_[1] - p_[0], p_[2] - p_[1], p_[3] - p_[2], p_[4] - p_[3]))
         print("  tile %2d | prod: start %6d emptywait %5d issue %5d | mma: tempty-wait %5d full-wait(1st) %5d mma+commit %5d | epi: tfull-wait %5d ld/res %5d compute %6d copyout %5d  [epi period %6d]" % (
             i, p_[0] - t0, p_[1] - p_[0], p_[2] - p_[1], m_[1] - m_[0], m_[2] - m_[1], m_[3] - m_[2],
             e_[1] - e_[0], e_[2] - e_[1], e_[3] - e_[2], e_[4] - e_[3], t[2, i, 4] - t[2, i - 1, 4]))
