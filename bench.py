@@ -70,9 +70,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=10.0):
+        """nvidia-smi needs a moment to start: block until the first sample arrived so that the timed region is covered."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples read between t_begin and t_end (perf_counter times of the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -81,7 +88,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.05)]
+        if not rows:
+            rows = [r for _, r in self.rows[-3:]]
+        for r in rows:
             f = [v.strip() for v in r.split(",")]
             if len(f) < 6:
                 continue
@@ -222,6 +232,10 @@ def run_ours(a):
         step(i, dev_pool)
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
+    if clocks is not None:
+        clocks.wait_first()
+    barrier()
+    t_begin = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(a.steps):
@@ -248,7 +262,7 @@ def run_ours(a):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
-    clk = clocks.stop() if clocks is not None else None
+    clk = clocks.stop(t_begin, time.perf_counter()) if clocks is not None else None
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:

@@ -46,22 +46,23 @@ constexpr int TC_EPI_RAW = 1;      // RAW_I32
 constexpr int TC_EPI_RES22 = 2;    // RESIDUAL: uint16 stream in, uint16 stream out
 constexpr int TC_EPI_RES44 = 3;    // RESIDUAL: int32 in (stream or identity-conv accumulator), int32 out
 constexpr int TC_EPI_RES42 = 4;    // RESIDUAL: int32 in, uint16 out
+constexpr int TC_EPI_DUAL = 5;     // RESIDUAL whose identity operand is a second in-kernel 1x1 convolution (two TMEM accumulators), uint16 out
 
 template <int BN, int EPI, bool A4 = false>
 struct TcSmem {
   // pipeline depth: RESIDUAL epilogues are epilogue-bound and need shared memory for their tiles; the others are
   // load-latency-bound and get a deep ring.  The producer keeps LAG + 1 k-tiles in flight per thread.
-  static constexpr int STAGES = (EPI == TC_EPI_RES22) ? (A4 && BN == 128 ? 4 : 5) : (EPI >= TC_EPI_RES44) ? 5 : (EPI == TC_EPI_RAW) ? 7 : (BN == 128 ? 8 : 10);
+  static constexpr int STAGES = (EPI == TC_EPI_RES22) ? (A4 && BN == 128 ? 4 : 5) : (EPI == TC_EPI_DUAL) ? 6 : (EPI >= TC_EPI_RES44) ? 5 : (EPI == TC_EPI_RAW) ? 7 : (BN == 128 ? 8 : 10);
   static constexpr int LAG = STAGES - 2;
   static constexpr int A_STAGE = TC_BM * 64;
   static constexpr int B_STAGE = BN * 64;
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int RING = STAGES * STAGE;
   static constexpr int CW = BN / 2;                                        // columns per epilogue warp
-  static constexpr int RES_ES = (EPI == TC_EPI_RES22) ? 2 : (EPI >= TC_EPI_RES44 ? 4 : 0);
-  static constexpr int Y_ES = (EPI == TC_EPI_RES22 || EPI == TC_EPI_RES42) ? 2 : ((EPI == TC_EPI_RES44 || EPI == TC_EPI_RAW) ? 4 : 0);
+  static constexpr int RES_ES = (EPI == TC_EPI_RES22) ? 2 : ((EPI == TC_EPI_RES44 || EPI == TC_EPI_RES42) ? 4 : 0);
+  static constexpr int Y_ES = (EPI == TC_EPI_RES22 || EPI == TC_EPI_RES42 || EPI == TC_EPI_DUAL) ? 2 : ((EPI == TC_EPI_RES44 || EPI == TC_EPI_RAW) ? 4 : 0);
   static constexpr int SLICE_ES = RES_ES > Y_ES ? RES_ES : Y_ES;
-  static constexpr bool TMA_IO = (EPI == TC_EPI_RES22);                    // residual tile in / outputs out as swizzled TMA boxes
+  static constexpr bool TMA_IO = (EPI == TC_EPI_RES22 || EPI == TC_EPI_DUAL);                    // residual tile in / outputs out as swizzled TMA boxes
   static constexpr int SLICE_PITCH = TMA_IO ? CW * SLICE_ES : CW * SLICE_ES + 16;   // padded: 16-byte row-per-lane accesses conflict-free
   static constexpr int SLICE = SLICE_ES ? (TMA_IO ? 4096 : 32 * SLICE_PITCH) : 0;
   static constexpr int SLICE_BUFS = (EPI == TC_EPI_RES22) ? 3 : 1;         // RES22: 2 prefetch + 1 output; RES4x: in place; RAW: output
@@ -70,9 +71,9 @@ struct TcSmem {
   static constexpr int SLICES_OFF = RING;
   static constexpr int LOW_OFF = SLICES_OFF + TC_EPI_WARPS * SLICE * SLICE_BUFS;
   static constexpr int CST_OFF = LOW_OFF + TC_EPI_WARPS * LOW_SLICE;       // double2 {Cb, M}[BN]
-  static constexpr int M1_OFF = CST_OFF + BN * 16;                         // double M1[BN]
+  static constexpr int M1_OFF = CST_OFF + BN * 16;                         // double M1[BN]  (DUAL: double2 {Cb2, M1}[BN])
   static constexpr int STG_SLOT = TC_BM * 32;                              // packed 4-bit rows of one k-tile (A4 only)
-  static constexpr int STG_OFF = M1_OFF + BN * 8;
+  static constexpr int STG_OFF = M1_OFF + BN * (EPI == TC_EPI_DUAL ? 16 : 8);
   static constexpr int PATCH_BUF = (EPI == TC_EPI_REQ) ? 256 * 64 : 0;      // 3x3 patch mode: two buffers of <= 256 pixel rows
   static constexpr int PATCH_OFF = STG_OFF + (A4 ? (LAG + 1) * STG_SLOT : 0);
   static constexpr int BAR_OFF = PATCH_OFF + 2 * PATCH_BUF;               // mbarriers + tmem base
@@ -215,9 +216,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   using S = TcSmem<BN, EPI, A4>;
   constexpr int BM = TC_BM, STAGES = S::STAGES, LAG = S::LAG;
   constexpr int CW = S::CW;                      // columns handled by one epilogue warp: 32 or 64
-  constexpr int TMEM_COLS = 2 * BN;              // two accumulator buffers (power of two >= 32: 128 / 256)
+  constexpr int TMEM_COLS = (EPI == TC_EPI_DUAL ? 4 : 2) * BN;   // two accumulator buffers (x2 accumulators in dual mode): 128 / 256 / 512
+  constexpr int ACC_STRIDE = (EPI == TC_EPI_DUAL ? 2 : 1) * BN;  // TMEM columns per buffer
   constexpr int RES_ES = S::RES_ES, Y_ES = S::Y_ES, PITCH = S::SLICE_PITCH;
   constexpr bool IS_RES = EPI >= TC_EPI_RES22;
+  constexpr bool DUAL = EPI == TC_EPI_DUAL;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps shared-space provenance
@@ -240,7 +243,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   };
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.Cout / BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int KT = p.KH * p.KW * p.cin_chunks;
+  const int KT1 = p.KH * p.KW * p.cin_chunks;                 // k-tiles of the main convolution
+  const int KT = KT1 + (DUAL ? p.cin_chunks2 : 0);            // + the identity-branch convolution (dual mode)
 
   // ---- one-time setup ----
   if (tid == 0) {
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         *reinterpret_cast<uint4*>(dst + (((2 * a_ch + 1) ^ sw) << 4)) = hi;
       }
     };
-    if (EPI == TC_EPI_REQ && p.patch_rows != 0) {
+    if (EPI == TC_EPI_REQ && p.patch_rows != 0) {   // (never in dual mode)
       // ---- 3x3 stride-1 pad-1: im2col from shared memory.  One TMA box per (tile, Cin chunk) brings the contiguous pixel
       // range [P0 - W - 1, P0 + 127 + W + 1] (zero-filled outside the tensor) into a patch buffer; for tap (kh, kw) output row
       // r needs patch row r + kh*W + kw.  Each producer thread copies (and for packed 4-bit input expands) its own row into
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
               if (tid == 0) {                                            // weights of this k-tile: K index = tap * Cin + c * 64
                 const int ktile = (kh * 3 + kw) * chunks + c;
                 mbar_arrive_expect_tx(full_bar(stage), S::B_STAGE);
-                if (p.w_tiled) bulk_load_1d(smem_base + stage * S::STAGE + S::A_STAGE, p.w_tiled + ((size_t)(n0 / BN) * KT + ktile) * S::B_STAGE, S::B_STAGE, full_bar(stage));
+                if (p.w_tiled) bulk_load_1d(smem_base + stage * S::STAGE + S::A_STAGE, p.w_tiled + ((size_t)(n0 / BN) * KT1 + ktile) * S::B_STAGE, S::B_STAGE, full_bar(stage));
                 else tma_load_2d(smem_base + stage * S::STAGE + S::A_STAGE, &maps.b, ktile * 64, n0, full_bar(stage));
               }
             }
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
             const uint32_t a_base = smem_base + stage * S::STAGE;
             mbar_arrive_expect_tx(full_bar(stage), S::A_STAGE + S::B_STAGE);
             tma_load_2d(a_base, &maps.a, kt * 64, m0, full_bar(stage));
-            if (p.w_tiled) bulk_load_1d(a_base + S::A_STAGE, p.w_tiled + ((size_t)(n0 / BN) * KT + kt) * S::B_STAGE, S::B_STAGE, full_bar(stage));
+            if (p.w_tiled) bulk_load_1d(a_base + S::A_STAGE, p.w_tiled + ((size_t)(n0 / BN) * KT1 + kt) * S::B_STAGE, S::B_STAGE, full_bar(stage));
             else tma_load_2d(a_base + S::A_STAGE, &maps.b, kt * 64, n0, full_bar(stage));
           }
         }
@@ -396,6 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
       int hi0[A_PASSES], wi0[A_PASSES], pix[A_PASSES];
+      int pix2[A_PASSES];                       // dual mode: identity-conv input pixel (1x1, pad 0, stride2)
       bool a_ok[A_PASSES];
 #pragma unroll
       for (int i = 0; i < A_PASSES; ++i) {
@@ -408,6 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         hi0[i] = ho * p.stride - p.pad;
         wi0[i] = wo * p.stride - p.pad;
         pix[i] = n * p.H * p.W;
+        pix2[i] = DUAL ? (n * p.H2 + ho * p.stride2) * p.W2 + wo * p.stride2 : 0;
       }
       int c = 0, kw = 0, kh = 0;
       const uint32_t ptile = (tile - blockIdx.x) / gridDim.x;
@@ -422,14 +428,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         for (int i = 0; i < A_PASSES; ++i) {
           const int row = tid / A_LPR + i * (128 / A_LPR);
           const int hi = hi0[i] + kh, wi = wi0[i] + kw;
-          const bool v = a_ok[i] && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W;
+          bool v = a_ok[i] && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W;
           const uint8_t* src = v ? p.x + (size_t)(pix[i] + hi * p.W + wi) * p.x_pix_bytes + c * (A4 ? 32 : 64) + a_ch * 16 : p.x;
+          if constexpr (DUAL) {
+            if (kt >= KT1) {                   // identity branch: k-tile (kt - KT1) of the second input tensor
+              v = a_ok[i];
+              src = v ? p.x2 + (size_t)pix2[i] * p.x2_pix_bytes + (kt - KT1) * (A4 ? 32 : 64) + a_ch * 16 : p.x;
+            }
+          }
           if constexpr (!A4) cp_async_16(a_base + swz<64>(row, a_ch), src, v ? 16 : 0);
           else cp_async_16(smem_base + S::STG_OFF + (it % (LAG + 1)) * S::STG_SLOT + row * 32 + a_ch * 16, src, v ? 16 : 0);
         }
         if (tid == 0) {                         // weights: one TMA box (64 x BN, SWIZZLE_64B) per k-tile
           mbar_arrive_expect_tx(full_bar(stage), S::B_STAGE);
-          if (p.w_tiled) bulk_load_1d(b_base, p.w_tiled + ((size_t)(n0 / BN) * KT + kt) * S::B_STAGE, S::B_STAGE, full_bar(stage));
+          if (DUAL && kt >= KT1) bulk_load_1d(b_base, p.w2_tiled + ((size_t)(n0 / BN) * p.cin_chunks2 + (kt - KT1)) * S::B_STAGE, S::B_STAGE, full_bar(stage));
+          else if (p.w_tiled) bulk_load_1d(b_base, p.w_tiled + ((size_t)(n0 / BN) * KT1 + kt) * S::B_STAGE, S::B_STAGE, full_bar(stage));
           else tma_load_2d(b_base, &maps.b, kt * 64, n0, full_bar(stage));
         }
         if constexpr (!A4) {
@@ -469,8 +482,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         mbar_wait(tempty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         trace(1, tile_iter, 1);
-        const uint32_t d_tmem = tmem_base + buf * BN;
+        const uint32_t d_tmem0 = tmem_base + buf * ACC_STRIDE;
         for (int kt = 0; kt < KT; ++kt, ++it) {
+          const uint32_t d_tmem = d_tmem0 + ((DUAL && kt >= KT1) ? BN : 0);     // dual mode: identity conv -> second accumulator
           const int stage = it % STAGES;
           mbar_wait(full_bar(stage), (it / STAGES) & 1);
           fence_proxy_async();            // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
@@ -480,7 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
           const uint32_t b_addr = a_addr + S::A_STAGE;
 #pragma unroll
           for (int k = 0; k < 2; ++k)
-            umma_i8(d_tmem, umma_desc_sw64(a_addr + k * 32), umma_desc_sw64(b_addr + k * 32), idesc, (kt | k) != 0);
+            umma_i8(d_tmem, umma_desc_sw64(a_addr + k * 32), umma_desc_sw64(b_addr + k * 32), idesc, (k != 0) || (kt != 0 && !(DUAL && kt == KT1)));
           umma_commit(empty_bar(stage));                          // smem stage reusable once these MMAs retire
           if (kt == KT - 1) { umma_commit(tfull_bar(buf)); trace(1, tile_iter, 3); }   // accumulator complete
         }
