@@ -61,6 +61,8 @@ SIGNATURES = {
     "hawq_conv2d": (_i32, _conv_args),
     "hawq_conv2d_i8": (_i32, _conv_args),
     "hawq_conv2d_i4": (_i32, _conv_args),
+    "hawq_conv2d_dual": (_i32, [_vp, C.POINTER(hawq_conv_desc), C.POINTER(hawq_epilogue_desc), _vp, _vp, _vp,
+                                C.POINTER(hawq_conv_desc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "hawq_linear_i8": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hawq_stem_conv_i8": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "hawq_maxpool_requant": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _u32, _i32, _i32, _i32, _vp, _vp]),

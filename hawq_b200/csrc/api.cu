@@ -154,7 +154,7 @@ int hawq_create(int device, hawq_handle** out) {
   CUDA_TRY(cudaMemset(h->status, 0, sizeof(int32_t)));
   int rc;
   if ((rc = set_tc_attr<TC_EPI_REQ>()) || (rc = set_tc_attr<TC_EPI_RAW>()) || (rc = set_tc_attr<TC_EPI_RES22>()) ||
-      (rc = set_tc_attr<TC_EPI_RES44>()) || (rc = set_tc_attr<TC_EPI_RES42>()))
+      (rc = set_tc_attr<TC_EPI_RES44>()) || (rc = set_tc_attr<TC_EPI_RES42>()) || (rc = set_tc_attr<TC_EPI_DUAL>()))
     return rc;
   if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
       (rc = set_conv_attr<64, true>()))
@@ -339,6 +339,70 @@ legacy:
     else launch_conv<64, true>(p, grid, s);
   }
   return launch_check("conv_igemm");
+}
+
+// Resize-unit fusion: y = RHE(m1 * (conv1x1_s(x2, w2) + bias2)) + RHE(m * (conv1x1(x, w) + bias)), ReLU, uint16 stream +
+// optional low-bit copy.  Both convolutions accumulate in TMEM inside one kernel (no int32 identity tensor in HBM).
+int hawq_conv2d_dual(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x, const int8_t* w,
+                     const hawq_chan* chan, const hawq_conv_desc* d2, const void* x2, const int8_t* w2, const hawq_chan* chan2,
+                     void* out, void* out_low, void* stream) {
+  if (!h || !d || !ep || !x || !w || !chan || !d2 || !x2 || !w2 || !chan2 || !out) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d_dual: null argument");
+  static const bool tc_enabled = [] { const char* e = getenv("HAWQ_B200_TC"); return !(e && e[0] == '0'); }();
+  static const bool dual_enabled = [] { const char* e = getenv("HAWQ_B200_DUAL"); return !(e && e[0] == '0'); }();
+  if (!tc_enabled || !dual_enabled) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: disabled by environment");
+  if (d->kh != 1 || d->kw != 1 || d->stride != 1 || d->pad != 0 || d2->kh != 1 || d2->kw != 1 || d2->pad != 0 || d2->stride < 1)
+    return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: both convolutions must be 1x1 without padding (main stride 1)");
+  if (d->N < 1 || d->H < 1 || d->W < 1 || d2->H < 1 || d2->W < 1) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d_dual: bad geometry");
+  if ((d->a_bits != 8 && d->a_bits != 4) || d2->a_bits != d->a_bits) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: a_bits must be equal and 4 or 8");
+  if (d->Cin % 64 || d2->Cin % 64 || d->Cout % 64 || d2->Cout != d->Cout) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: channel counts must be multiples of 64 and Cout equal");
+  if (d2->N != d->N || (d2->H - 1) / d2->stride + 1 != d->H || (d2->W - 1) / d2->stride + 1 != d->W)
+    return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d_dual: the two convolutions have different output grids");
+  if (d->w_layout != 1 || d2->w_layout != 1) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: weights must carry the re-tiled copy (w_layout 1)");
+  if (ep->mode != HAWQ_EPI_RESIDUAL || !ep->relu || ep->y_bits != 16) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: RESIDUAL + relu + uint16 stream only");
+  if (ep->low_bits != 0 && ep->low_bits != 4 && ep->low_bits != 8) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d_dual: low_bits must be 0/4/8");
+  if (ep->low_bits) {
+    if (!out_low) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d_dual: low_bits set but out_low is null");
+    int rc = check_me(ep->low_m, ep->low_e, "hawq_conv2d_dual low-bit copy");
+    if (rc) return rc;
+    if (!dyadic_is_fast(ep->low_m, ep->low_e)) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: low-bit ratio outside the fast range");
+  }
+  const bool ratios_one = (ep->flags & HAWQ_EP_RATIOS_LE_ONE) != 0;
+  const bool ratios_wide = !ratios_one && (ep->flags & HAWQ_EP_RATIOS_LE_2P20) != 0;
+  if (!ratios_one && !ratios_wide) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: needs a ratio-range promise (flags)");
+  const long long M = (long long)d->N * d->H * d->W;
+  if (M > 0x7fffff00ll || (long long)d2->N * d2->H * d2->W > 0x7fffff00ll) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: too many pixels");
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const uint8_t*)x; p.w = w; p.chan = chan; p.out = out; p.out_low = out_low; p.status = h->status;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.KH = 1; p.KW = 1; p.stride = 1; p.pad = 0;
+  p.Ho = d->H; p.Wo = d->W; p.M = (int)M; p.K = d->Cin; p.cin_chunks = d->Cin / 64; p.x_pix_bytes = d->Cin * d->a_bits / 8;
+  p.mode = ep->mode; p.relu = 1; p.res_kind = 1; p.y_bits = 16; p.low_bits = ep->low_bits; p.low_m = ep->low_m; p.low_e = ep->low_e;
+  p.low_lo = ep->low_lo; p.low_hi = ep->low_hi;
+  p.trace = g_trace;
+  p.w_tiled = w + (size_t)d->Cout * d->Cin;
+  p.dual = 1;
+  p.x2 = (const uint8_t*)x2; p.w2_tiled = w2 + (size_t)d2->Cout * d2->Cin; p.chan2 = chan2;
+  p.H2 = d2->H; p.W2 = d2->W; p.stride2 = d2->stride; p.cin_chunks2 = d2->Cin / 64; p.x2_pix_bytes = d2->Cin * d2->a_bits / 8;
+  p.tma_io = 1;
+
+  const bool a4 = d->a_bits == 4;
+  const bool bn128 = (d->Cout % 128 == 0);
+  const uint32_t cw = (bn128 ? 128 : 64) / 2;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const CUtensorMapSwizzle sw_y = cw * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  int bad = make_map_2d(&maps.y, out, (uint64_t)d->Cout * 2, (uint64_t)M, (uint64_t)d->Cout * 2, cw * 2, 32, sw_y);
+  if (ep->low_bits) {
+    const uint32_t lb = cw * ep->low_bits / 8;
+    const CUtensorMapSwizzle sw_l = lb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : lb == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    bad |= make_map_2d(&maps.low, out_low, (uint64_t)d->Cout * ep->low_bits / 8, (uint64_t)M, (uint64_t)d->Cout * ep->low_bits / 8, lb, 32, sw_l);
+  }
+  if (bad) return fail(HAWQ_ERR_CUDA, "hawq_conv2d_dual: cuTensorMapEncodeTiled failed");
+  const long long tiles = ((M + TC_BM - 1) / TC_BM) * (d->Cout / (bn128 ? 128 : 64));
+  const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+  launch_tc<TC_EPI_DUAL>(p, maps, bn128, ratios_wide, a4, grid, (cudaStream_t)stream);
+  return launch_check("conv_tc_dual");
 }
 
 int hawq_conv2d_i8(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x,

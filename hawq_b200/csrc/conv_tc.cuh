@@ -163,6 +163,15 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
       : "memory");
 }
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives row (lane quarter base + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -227,6 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   const uint32_t smem_base = smem_u32(smem);
   double2* sCst = reinterpret_cast<double2*>(smem + S::CST_OFF);
   double* sM1 = reinterpret_cast<double*>(smem + S::M1_OFF);
+  double2* sCst2 = reinterpret_cast<double2*>(smem + S::M1_OFF);   // dual mode: {Cb2, M1} of the identity convolution
   const uint32_t bar_base = smem_base + S::BAR_OFF;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -536,7 +546,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       }
     };
     auto prefetch_residual = [&](int tile, uint8_t* dst) {
-      if constexpr (IS_RES) {
+      if constexpr (IS_RES && !DUAL) {
         const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
         const uint8_t* gres = reinterpret_cast<const uint8_t*>(p.res) + ((size_t)(m0 + quarter * 32) * p.Cout + n0 + half * CW) * RES_ES;
         const int rows_ok = p.M - (m0 + quarter * 32);
@@ -569,7 +579,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
           const hawq_chan ch = p.chan[n0 + i];
           sCst[i] = make_double2(kOffS - (double)ch.bias, dyadic_to_double(ch.m, ch.e));
           bad |= !ratio_ok(ch.m, ch.e) | (ch.bias >= (1 << 29)) | (ch.bias <= -(1 << 29));
-          if constexpr (EPI >= TC_EPI_RES44) {
+          if constexpr (DUAL) {
+            const hawq_chan rc = p.chan2[n0 + i];
+            sCst2[i] = make_double2(kOffS - (double)rc.bias, dyadic_to_double(rc.m, rc.e));
+            bad |= !ratio_ok(rc.m, rc.e) | (rc.bias >= (1 << 29)) | (rc.bias <= -(1 << 29));
+          } else if constexpr (EPI >= TC_EPI_RES44) {
             if (p.res_kind == 1) {
               const hawq_chan rc = p.res_chan[n0 + i];
               sM1[i] = dyadic_to_double(rc.m, rc.e);
@@ -586,7 +600,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       if constexpr (EPI == TC_EPI_RES22) {         // this tile's residual was prefetched; start the next one
         const int nxt = tile + gridDim.x;
         if (nxt < num_tiles) prefetch_residual_tma(nxt, tile_iter + 1);
-      } else if constexpr (IS_RES) {        // in-place variant (copy-out of the previous tile is synchronous)
+      } else if constexpr (IS_RES && !DUAL) {        // in-place variant (copy-out of the previous tile is synchronous)
         prefetch_residual(tile, rslice);
       }
 
@@ -596,6 +610,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       if (ew == 0) trace(2, tile_iter, 1);
       if constexpr (EPI == TC_EPI_RES22) {
         mbar_wait(res_bar(ew, tile_iter & 1), (tile_iter >> 1) & 1);     // residual tile landed (TMA)
+        if (lane == 0) bulk_wait_read_all();                            // previous tile's TMA stores have read y / low tiles
+      } else if constexpr (DUAL) {
         if (lane == 0) bulk_wait_read_all();                            // previous tile's TMA stores have read y / low tiles
       } else if constexpr (IS_RES) {
         cp_async_wait<0>();
@@ -607,7 +623,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
 #pragma unroll
       for (int cb = 0; cb < CW; cb += 32) {
         uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + half * CW + cb, acc);
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * ACC_STRIDE + half * CW + cb, acc);
         tmem_ld_wait();
         const double2* cst = sCst + half * CW + cb;
         if constexpr (EPI == TC_EPI_REQ) {
@@ -644,11 +660,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
 #pragma unroll
           for (int j = 0; j < 32; j += 16) {
             uint32_t lw[4];
+            uint32_t acc2[16];               // dual mode: identity-conv accumulator columns cb + j .. + 15
+            if constexpr (DUAL) {
+              tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * ACC_STRIDE + BN + half * CW + cb + j, acc2);
+              tmem_ld_wait();
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int jj = j + h * 8;
               int r[8];
-              if constexpr (RES_ES == 2) {
+              if constexpr (DUAL) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] = (int)acc2[h * 8 + k];
+              } else if constexpr (RES_ES == 2) {
                 const uint4 pr = *reinterpret_cast<const uint4*>(rslice + tma_tile_off(RB, lane, (cb + jj) >> 3));
                 r[0] = pr.x & 0xFFFF; r[1] = pr.x >> 16; r[2] = pr.y & 0xFFFF; r[3] = pr.y >> 16;
                 r[4] = pr.z & 0xFFFF; r[5] = pr.z >> 16; r[6] = pr.w & 0xFFFF; r[7] = pr.w >> 16;
@@ -664,9 +688,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
                 const double d = __hiloint2double(0x43300000, acc[jj + k] ^ 0x80000000) - cm.x;
                 const double qv = __fma_rn(d, cm.y, kMagic);
                 const int v = __double2loint(qv);
-                const double dr = (RES_ES == 2) ? (__hiloint2double(0x43300000, r[k]) - kOffU)
-                                                : (__hiloint2double(0x43300000, r[k] ^ 0x80000000) - kOffS);
-                const double qr = __fma_rn(dr, (EPI == TC_EPI_RES22) ? res_M : m1[jj + k], kMagic);
+                double dr, mr;
+                if constexpr (DUAL) {          // identity accumulator + its bias, per-channel ratio
+                  const double2 c2 = sCst2[half * CW + cb + jj + k];
+                  dr = __hiloint2double(0x43300000, r[k] ^ 0x80000000) - c2.x;
+                  mr = c2.y;
+                } else {
+                  dr = (RES_ES == 2) ? (__hiloint2double(0x43300000, r[k]) - kOffU) : (__hiloint2double(0x43300000, r[k] ^ 0x80000000) - kOffS);
+                  mr = (EPI == TC_EPI_RES22) ? res_M : m1[jj + k];
+                }
+                const double qr = __fma_rn(dr, mr, kMagic);
                 const int vr = __double2loint(qr);
                 const int sum = v + vr;
                 if constexpr (WIDE) {
@@ -698,14 +729,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
                 o.y = __byte_perm(min(y[2], 65535), min(y[3], 65535), 0x5410);
                 o.z = __byte_perm(min(y[4], 65535), min(y[5], 65535), 0x5410);
                 o.w = __byte_perm(min(y[6], 65535), min(y[7], 65535), 0x5410);
-                if constexpr (EPI == TC_EPI_RES22) *reinterpret_cast<uint4*>(yslice + tma_tile_off(RB, lane, (cb + jj) >> 3)) = o;
+                if constexpr (S::TMA_IO) *reinterpret_cast<uint4*>(yslice + tma_tile_off(RB, lane, (cb + jj) >> 3)) = o;
                 else *reinterpret_cast<uint4*>(myy + (cb + jj) * 2) = o;
               } else {
                 *reinterpret_cast<int4*>(myy + (cb + jj) * 4) = make_int4(y[0], y[1], y[2], y[3]);
                 *reinterpret_cast<int4*>(myy + (cb + jj) * 4 + 16) = make_int4(y[4], y[5], y[6], y[7]);
               }
             }
-            if constexpr (EPI == TC_EPI_RES22) {   // dense swizzled low tile (TMA box): 8-bit rows of CW bytes, 4-bit rows of CW/2 bytes
+            if constexpr (S::TMA_IO) {   // dense swizzled low tile (TMA box): 8-bit rows of CW bytes, 4-bit rows of CW/2 bytes
               if (low_bits == 8) *reinterpret_cast<uint4*>(lowslice + tma_tile_off(CW, lane, (cb + j) >> 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
               else if (low_bits == 4) *reinterpret_cast<uint2*>(lowslice + tma_tile_off(CW / 2, lane, (cb + j) >> 5) + (((cb + j) >> 1) & 8)) = make_uint2(lw[0], lw[1]);
             } else {
@@ -722,7 +753,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       if (ew == 0) trace(2, tile_iter, 3);
 
       const int rows_ok = p.M - (m0 + quarter * 32);
-      if constexpr (EPI == TC_EPI_RES22) {
+      if constexpr (S::TMA_IO) {
         // TMA tile stores: every lane publishes its writes to the async proxy, one lane issues two box stores (rows past M
         // are clipped by the tensor map); they drain while the next tile is computed
         fence_proxy_async();
@@ -780,7 +811,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       }
       if (ew == 0) trace(2, tile_iter, 4);
     }
-    if constexpr (EPI == TC_EPI_RES22) {
+    if constexpr (S::TMA_IO) {
       if (lane == 0) bulk_wait_all();
     }
     if constexpr (IS_RES) {

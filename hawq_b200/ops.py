@@ -143,6 +143,22 @@ def conv2d(x, desc, ep, w, chan, res=None, res_chan=None, fscale=None, out=None,
     _count("hawq_conv2d", conv_work(desc, ep) if ev is not None else None, ev)
 
 
+def conv2d_dual(x, desc, ep, w, chan, desc2, x2, w2, chan2, out=None, out_low=None):
+    """resize unit: identity 1x1 conv (desc2/x2/w2/chan2) + last 1x1 conv (desc/x/w/chan) + case-1 sum in one kernel."""
+    h, s = _ctx(x)
+    ev = _begin()
+    _lib.check(_lib.load().hawq_conv2d_dual(h, C.byref(desc), C.byref(ep), _p(x), _p(w), _p(chan), C.byref(desc2), _p(x2), _p(w2),
+                                            _p(chan2), _p(out), _p(out_low), s))
+    work = None
+    if ev is not None:
+        m = desc.N * desc.H * desc.W
+        macs = m * desc.Cout * (desc.Cin + desc2.Cin)
+        b = (m * (desc.Cin + desc2.Cin) * desc.a_bits // 8 + desc.Cout * (desc.Cin + desc2.Cin) + 32 * desc.Cout
+             + m * desc.Cout * (ep.y_bits + ep.low_bits) // 8)
+        work = (macs, b)
+    _count("hawq_conv2d_dual", work, ev)
+
+
 def linear(x, w, chan, fscale, out, n, k, cout, cout_pad):
     h, s = _ctx(x)
     ev = _begin()

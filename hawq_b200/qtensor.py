@@ -14,6 +14,8 @@ unit's low-bit activation) folded into the kernel epilogue.
 ``__torch_function__`` and recorded on the node; anything else is not an integer-path operation and raises.
 """
 import numpy as np
+import os
+
 import torch
 
 from . import ops, quant_math as qmath
@@ -24,6 +26,7 @@ class EngineConfig:
     """residual_bits: storage of the post-ReLU residual stream: 32 (always exact) or 16 (uint16 + sticky overflow
     flag HAWQ_FLAG_RESIDUAL_OVERFLOW; ``CompiledModel`` re-runs in 32-bit mode when the flag is raised)."""
     residual_bits = 32
+    dual = os.environ.get("HAWQ_B200_DUAL", "1") != "0"   # resize units: identity conv + last conv in one kernel (uint16 stream only)
 
 
 config = EngineConfig()
@@ -339,12 +342,21 @@ def _launch_residual(r, low_act, device):
     chan = _chan_tensor(ent, _act_tag("c1", act), m2, e2, device)
     res_chan = None
     pairs = [(m2, e2)]
+    dual = None
     if ident.kind == "conv":
-        res, ient = _conv_raw(ident, device)
+        _check_src(ident)
+        ient = _conv_cache(ident.mod, ident.a_sf, ident.src.bits, device)
         m1, e1 = _dyadic(act, id_sf, id_w_sf, "case1-idconv")
         res_chan = _chan_tensor(ient, _act_tag("c1res", act), m1, e1, device)
         res_kind, res_bits, res_me = 1, 32, (0, 1)
         pairs.append((m1, e1))
+        # resize units: both 1x1 convolutions in one kernel (two TMEM accumulators) when the fast uint16 stream is in use
+        if (config.dual and r.relu and config.residual_bits == 16 and ent["k"] == 1 and ent["stride"] == 1 and ent["pad"] == 0
+                and ient["k"] == 1 and ient["pad"] == 0 and ent["w_layout"] == 1 and ient["w_layout"] == 1
+                and conv.src.bits == ident.src.bits):
+            dual = ient
+        else:
+            res, _ = _conv_raw(ident, device)
     else:
         ident = materialize(ident, device)
         if ident.bits not in (16, 32):
@@ -370,7 +382,17 @@ def _launch_residual(r, low_act, device):
                         signed=(low_act.quant_mode == "symmetric"))
     ep = ops.epilogue(EPI_RESIDUAL, relu=r.relu, res_kind=res_kind, res_bits=res_bits, res_me=res_me, y_bits=y_bits,
                       flags=ops.ratio_flags(*pairs), **kw)
-    _launch_conv(conv, ent, ep, chan, device, out=y, out_low=low, res=res, res_chan=res_chan)
+    if dual is not None and ep.flags == 0:       # no ratio promise (saturating generic kernels): two launches
+        res, _ = _conv_raw(ident, device)
+        dual = None
+    if dual is not None:
+        nb2, hh2, ww2, _, _ = _conv_out_hw(ident, dual)
+        _, hh, ww, _, _ = _conv_out_hw(conv, ent)
+        d1 = ops.conv_desc(nb, hh, ww, ent["cin"], ent["cout"], 1, 1, 1, 0, conv.src.bits, 1)
+        d2 = ops.conv_desc(nb2, hh2, ww2, dual["cin"], dual["cout"], 1, 1, dual["stride"], 0, ident.src.bits, 1)
+        ops.conv2d_dual(conv.src.data, d1, ep, ent["w"], chan, d2, ident.src.data, dual["w"], res_chan, out=y, out_low=low)
+    else:
+        _launch_conv(conv, ent, ep, chan, device, out=y, out_low=low, res=res, res_chan=res_chan)
     r.shape = (nb, ent["cout"], ho, wo)
     r.become_int(y, y_bits, signed=(y_bits == 32))
     return low_node

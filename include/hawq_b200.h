@@ -136,6 +136,18 @@ int hawq_conv2d_i4(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_
                    const void* res, const hawq_chan* res_chan, const float* fscale,
                    void* out, void* out_low, void* stream);
 
+/* Resize residual units (Q_ResUnitBn with resize_identity, q_resnet.py:304-330): the identity-branch 1x1 convolution
+ * (d2/x2/w2; stride d2->stride, pad 0) and the unit's last 1x1 convolution (d/x/w; stride 1) are accumulated side by side in
+ * one kernel and combined by the case-1 fixed-point sum (quant_utils.py:430-456):
+ *   y = ReLU( RHE((acc2 + chan2.bias) * chan2.m / 2^chan2.e) + RHE((acc + chan.bias) * chan.m / 2^chan.e) )
+ * ep: mode RESIDUAL, relu 1, y_bits 16 (uint16 stream in out), optional low-bit copy in out_low, flags = ratio promise.
+ * Both descriptors need w_layout 1 and equal a_bits / Cout / output grids.  Returns HAWQ_ERR_UNSUPPORTED for any other
+ * combination (callers then use hawq_conv2d RAW_I32 followed by hawq_conv2d RESIDUAL res_kind 1: same results). */
+int hawq_conv2d_dual(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_desc* ep,
+                     const void* x, const int8_t* w, const hawq_chan* chan,
+                     const hawq_conv_desc* d2, const void* x2, const int8_t* w2, const hawq_chan* chan2,
+                     void* out, void* out_low, void* stream);
+
 /* QuantLinear.forward (quant_modules.py:79-130): x int8 [N,K], w int8 [Cout_pad,K] (rows >= Cout zero),
  * chan[Cout_pad] (bias only), fscale[Cout_pad] = fc_scaling_factor[c] * act_scale (fp32 product) -> fp32 [N,Cout]. */
 int hawq_linear_i8(hawq_handle* h, int32_t N, int32_t K, int32_t Cout, int32_t Cout_pad,

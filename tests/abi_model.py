@@ -126,6 +126,16 @@ def conv2d(x, desc, ep, w, chan, res=None, res_chan=None, fscale=None, out=None,
         out.view(-1, ep.cout_store).copy_(torch.from_numpy(np.ascontiguousarray(o)))
 
 
+def conv2d_dual(x, desc, ep, w, chan, desc2, x2, w2, chan2, out=None, out_low=None):
+    """hawq_conv2d_dual == RAW_I32 identity convolution followed by the res_kind 1 RESIDUAL convolution."""
+    m = desc.N * desc.H * desc.W
+    raw = torch.empty(m * desc.Cout, dtype=torch.int32)
+    conv2d(x2, desc2, real_ops.epilogue(EPI_RAW_I32), w2, chan2, out=raw)
+    ep1 = real_ops.epilogue(EPI_RESIDUAL, relu=ep.relu, res_kind=1, res_bits=32, y_bits=ep.y_bits, low_bits=ep.low_bits,
+                            low_me=(ep.low_m, ep.low_e), low_clamp=(ep.low_lo, ep.low_hi), flags=ep.flags)
+    conv2d(x, desc, ep1, w, chan, res=raw, res_chan=chan2, out=out, out_low=out_low)
+
+
 def linear(x, w, chan, fscale, out, n, k, cout, cout_pad):
     d = real_ops.conv_desc(n, 1, 1, k, cout_pad, 1, 1, 1, 0, 8)
     conv2d(x, d, real_ops.epilogue(EPI_DEQUANT_F32, cout_store=cout), w, chan, fscale=fscale, out=out)
@@ -211,7 +221,7 @@ def install_cpu_backend(monkeypatch):
     """Route hawq_b200.ops launchers to this model (CPU tensors).  Test-only."""
     from hawq_b200 import ops
     status["flags"] = 0
-    for name, fn in dict(conv2d=conv2d, linear=linear, stem_conv=stem_conv, maxpool_requant=maxpool_requant,
+    for name, fn in dict(conv2d=conv2d, conv2d_dual=conv2d_dual, linear=linear, stem_conv=stem_conv, maxpool_requant=maxpool_requant,
                          avgpool_requant=avgpool_requant, quantize_input=quantize_input, requant=requant,
                          add_requant=add_requant, dequant=dequant, pack_i4=pack_i4_op, unpack_i4=unpack_i4_op).items():
         monkeypatch.setattr(ops, name, fn)

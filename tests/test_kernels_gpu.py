@@ -182,6 +182,62 @@ def test_conv_residual_wide_ratios_on_tensor_cores(geom):
     ops.reset_status(0)
 
 
+DUAL_GEOMS = [
+    # N, Ho, Wo, Cin (last conv), Cin2 (identity conv), Cout, identity stride
+    (2, 7, 7, 64, 64, 256, 1),         # ResNet-50 stage-1 shape: M = 98 (< one tile), 2 column tiles of 128
+    (3, 5, 7, 128, 256, 512, 2),       # stride-2 identity, M = 105
+    (2, 12, 12, 64, 128, 192, 2),      # Cout = 192 -> BN = 64, M = 288: 3 row tiles, ragged last
+    (1, 9, 16, 192, 64, 128, 1),       # 3 + 1 k-tiles
+]
+
+
+@pytest.mark.parametrize("flag", [1, 2])
+@pytest.mark.parametrize("a_bits", [8, 4])
+@pytest.mark.parametrize("geom", DUAL_GEOMS)
+def test_conv_dual_resize_unit(geom, a_bits, flag):
+    """hawq_conv2d_dual (two TMEM accumulators) == RAW_I32 identity conv + res_kind-1 RESIDUAL conv of the ABI model."""
+    n, ho, wo, cin, cin2, cout, s2 = geom
+    r = rng(777 + sum(v * (i + 3) for i, v in enumerate(geom)) * 4 + a_bits + flag)
+    h2, w2 = (ho - 1) * s2 + 1 + (s2 - 1), (wo - 1) * s2 + 1     # one extra (unused) row for strided inputs
+    assert (h2 - 1) // s2 + 1 == ho and (w2 - 1) // s2 + 1 == wo
+    numel = n * ho * wo * cout
+    x = rand_act(r, n * ho * wo * cin, a_bits)
+    x2 = rand_act(r, n * h2 * w2 * cin2, a_bits)
+    wt = torch.from_numpy(r.randint(-8, 8, size=(cout, 1, 1, cin)).astype(np.int8))
+    wt2 = torch.from_numpy(r.randint(-8, 8, size=(cout, 1, 1, cin2)).astype(np.int8))
+    if a_bits == 4:
+        ops.permute_weights_for_i4(wt)
+        ops.permute_weights_for_i4(wt2)
+    hi = 0.9 if flag == 1 else 30.0
+    chan = make_chan(r, cout, bias_mag=3000, ratio_lo=1e-2, ratio_hi=hi)
+    chan2 = make_chan(r, cout, bias_mag=3000, ratio_lo=1e-2, ratio_hi=hi)
+    d = ops.conv_desc(n, ho, wo, cin, cout, 1, 1, 1, 0, a_bits, 1)
+    d2 = ops.conv_desc(n, h2, w2, cin2, cout, 1, 1, s2, 0, a_bits, 1)
+    wg, wg2 = ops.upload_weights(wt, DEV), ops.upload_weights(wt2, DEV)
+    for low_bits in (8, 4, 0):
+        ep = ops.epilogue(EPI_RESIDUAL, relu=1, res_kind=1, res_bits=32, y_bits=16, low_bits=low_bits, low_me=dyadic(0.003),
+                          low_clamp=(0, 15) if low_bits == 4 else (-128, 127), flags=flag)
+        args = dict(x=x, desc=d, ep=ep, w=wt, chan=chan, desc2=d2, x2=x2, w2=wt2, chan2=chan2, out=out_buf(numel, 16),
+                    out_low=out_buf(numel, low_bits) if low_bits else None)
+        keys = ["out"] + (["out_low"] if low_bits else [])
+        ops.reset_status(0)
+        cs, gs = run_both("conv2d_dual", args, keys, gpu_overrides=dict(w=wg, w2=wg2))
+        assert ops.get_status(0) & 6 == 0
+        for a, b, k_ in zip(cs, gs, keys):
+            assert torch.equal(a, b), (geom, a_bits, flag, low_bits, k_)
+    ops.reset_status(0)
+
+
+def test_conv_dual_rejects_unsupported():
+    d = ops.conv_desc(1, 4, 4, 64, 64, 1, 1, 1, 0, 8, 0)       # w_layout 0: no re-tiled copy
+    ep = ops.epilogue(EPI_RESIDUAL, relu=1, res_kind=1, res_bits=32, y_bits=16, flags=1)
+    z = torch.zeros(64 * 64 * 2, dtype=torch.int8, device=DEV)
+    ch = torch.zeros(64, 4, dtype=torch.int32, device=DEV)
+    y = torch.zeros(16 * 64, dtype=torch.int16, device=DEV)
+    with pytest.raises(HawqError):
+        ops.conv2d_dual(z, d, ep, z, ch, d, z, z, ch, out=y)
+
+
 def test_residual_overflow_flag():
     r = rng(5)
     n, h, w, cin, cout = 1, 4, 4, 64, 64
