@@ -44,6 +44,7 @@ FLAG_BAD_RATIO = 2
 FLAG_REQUANT_OVERFLOW = 4
 EP_RATIOS_LE_ONE = 1
 EP_RATIOS_LE_2P20 = 2
+ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA = -1, -2, -3   # hawq_status
 
 _vp, _i32, _i64, _u32, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float
 _conv_args = [_vp, C.POINTER(hawq_conv_desc), C.POINTER(hawq_epilogue_desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]

@@ -191,6 +191,14 @@ int hawq_copy_status(hawq_handle* h, int32_t* dst, void* stream) {
   return HAWQ_OK;
 }
 
+static bool sat_pack_enabled() {
+  static const bool on = [] { const char* e = getenv("HAWQ_B200_SATPACK"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+// scalar dyadic pairs whose folded FMA constant (magic - 2^52 * m * 2^-e) is exact in the tcgen05 RESIDUAL epilogues
+static bool fold_ok(uint32_t m, int e) { return m == 0u || e <= 51; }
+
 static int check_me(uint32_t m, int e, const char* what) {
   if (e < 1 || e > 62 || m > 0x80000000u) return fail(HAWQ_ERR_BAD_ARG, "%s: dyadic pair out of range (m=%u e=%d)", what, m, e);
   return HAWQ_OK;
@@ -229,6 +237,7 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   p.tma_io = 0;
   p.patch_rows = 0;
   p.w_tiled = nullptr;
+  p.sat_pack = sat_pack_enabled() ? 1 : 0;
   if (ep->mode == HAWQ_EPI_RESIDUAL) {
     if (ep->res_kind == 0 && !dyadic_is_fast(ep->res_m, ep->res_e)) p.slow_scalar = 1;
     if (ep->low_bits != 0 && !dyadic_is_fast(ep->low_m, ep->low_e)) p.slow_scalar = 1;
@@ -278,7 +287,8 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
                       ep->mode == HAWQ_EPI_RAW_I32;
   const bool ratios_one = (ep->flags & HAWQ_EP_RATIOS_LE_ONE) != 0;
   const bool ratios_wide = !ratios_one && (ep->flags & HAWQ_EP_RATIOS_LE_2P20) != 0 && ep->mode == HAWQ_EPI_RESIDUAL;
-  if (tc_enabled && tc_epi && (ratios_one || ratios_wide)) {
+  const bool folds = ep->mode != HAWQ_EPI_RESIDUAL || ((ep->res_kind != 0 || fold_ok(ep->res_m, ep->res_e)) && (ep->low_bits == 0 || fold_ok(ep->low_m, ep->low_e)));
+  if (tc_enabled && tc_epi && folds && (ratios_one || ratios_wide)) {
     const bool a4 = d->a_bits == 4;
     const int bn = (d->Cout % 128 == 0) ? 128 : 64;
     TcMaps maps;
@@ -364,7 +374,7 @@ int hawq_conv2d_dual(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogu
     if (!out_low) return fail(HAWQ_ERR_BAD_ARG, "hawq_conv2d_dual: low_bits set but out_low is null");
     int rc = check_me(ep->low_m, ep->low_e, "hawq_conv2d_dual low-bit copy");
     if (rc) return rc;
-    if (!dyadic_is_fast(ep->low_m, ep->low_e)) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: low-bit ratio outside the fast range");
+    if (!dyadic_is_fast(ep->low_m, ep->low_e) || !fold_ok(ep->low_m, ep->low_e)) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: low-bit ratio outside the fast range");
   }
   const bool ratios_one = (ep->flags & HAWQ_EP_RATIOS_LE_ONE) != 0;
   const bool ratios_wide = !ratios_one && (ep->flags & HAWQ_EP_RATIOS_LE_2P20) != 0;
@@ -382,6 +392,7 @@ int hawq_conv2d_dual(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogu
   p.trace = g_trace;
   p.w_tiled = w + (size_t)d->Cout * d->Cin;
   p.dual = 1;
+  p.sat_pack = sat_pack_enabled() ? 1 : 0;
   p.x2 = (const uint8_t*)x2; p.w2_tiled = w2 + (size_t)d2->Cout * d2->Cin; p.chan2 = chan2;
   p.H2 = d2->H; p.W2 = d2->W; p.stride2 = d2->stride; p.cin_chunks2 = d2->Cin / 64; p.x2_pix_bytes = d2->Cin * d2->a_bits / 8;
   p.tma_io = 1;

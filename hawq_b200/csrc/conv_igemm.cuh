@@ -46,6 +46,7 @@ struct ConvParams {
   int patch_rows;    // tcgen05 kernel, 3x3 stride-1 pad-1 layers: rows of the shared-memory input patch (128 + 2W + 2), 0 = gather mode
   // tcgen05 dual mode (resize units): the identity-branch 1x1 convolution is computed in the same kernel into a second
   // TMEM accumulator instead of round-tripping an int32 tensor through HBM
+  int sat_pack;           // tcgen05 RESIDUAL epilogues: 8-bit low copy packed with cvt.pack.sat when its clamp is [<= 0, 127]
   int dual;               // 0 / 1
   const uint8_t* x2;      // identity conv input (same a_bits as x)
   const int8_t* w2_tiled; // its re-tiled weights

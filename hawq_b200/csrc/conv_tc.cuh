@@ -522,20 +522,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     uint8_t* myy = yslice + lane * PITCH;
     uint8_t* mylow = lowslice + lane * S::LOW_PITCH;
     const int low_bits = IS_RES ? p.low_bits : (EPI == TC_EPI_REQ ? p.out_bits : 0);
-    const int low_row_bytes = low_bits == 8 ? CW : CW / 2;
+    constexpr double kMagic = 6755399441055744.0, kOffS = 4503601774854144.0, kOffU = 4503599627370496.0;
     const double low_M = dyadic_to_double(p.low_m, p.low_e);
     const double res_M = dyadic_to_double(p.res_m, p.res_e);
+    // unsigned operands (uint16 residual, post-ReLU sum): u * M + magic == fma(2^52 + u, M, magic - 2^52 * M) with a single
+    // rounding of the same real number, as long as the folded constant is exact (e <= 51, checked below): saves one DADD each
+    const double low_C = kMagic - kOffU * low_M;
+    const double res_C = kMagic - kOffU * res_M;
+    // post-ReLU values requantised with a ratio >= 0 are >= 0: with clamp [<= 0, 127] the clamp is the s8 saturation of cvt.pack
+    const bool sat8 = IS_RES && p.sat_pack != 0 && p.low_bits == 8 && p.low_hi == 127 && p.low_lo <= 0;
     const int q_lo = (EPI == TC_EPI_REQ) ? (p.relu ? max(p.lo, 0) : p.lo) : p.low_lo;
     const int q_hi = (EPI == TC_EPI_REQ) ? p.hi : p.low_hi;
-    constexpr double kMagic = 6755399441055744.0, kOffS = 4503601774854144.0, kOffU = 4503599627370496.0;
     constexpr int RES_CPR = CW * RES_ES / 16;    // 16-byte chunks per residual row
     int ymax = 0, ovf = 0;
     int bad = (IS_RES && !p.relu) ? 1 : 0;
     int cur_n0 = -1;
     uint32_t tile_iter = 0;
     auto ratio_ok = [](uint32_t m, int e) { return m == 0u || e >= (WIDE ? 11 : 31); };
-    if (IS_RES && p.res_kind == 0) bad |= !ratio_ok(p.res_m, p.res_e);
-    if (low_bits && IS_RES) bad |= !dyadic_is_fast(p.low_m, p.low_e);
+    if (IS_RES && p.res_kind == 0) bad |= !ratio_ok(p.res_m, p.res_e) | (p.res_m != 0u && p.res_e > 51);
+    if (low_bits && IS_RES) bad |= !dyadic_is_fast(p.low_m, p.low_e) | (p.low_m != 0u && p.low_e > 51);
 
     constexpr int RB = CW * 2;                  // RES22 tile row bytes (uint16)
     auto prefetch_residual_tma = [&](int tile, uint32_t k) {      // k-th tile of this CTA -> buffer k & 1
@@ -559,6 +564,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
         }
       }
       cp_async_commit();
+    };
+    // two values -> two uint16 halves with unsigned saturation (lo in the low half)
+    auto pack2_sat_u16 = [](int lo, int hi) {
+      uint32_t out;
+      asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(out) : "r"(hi), "r"(lo));
+      return out;
+    };
+    // pack 4 values into 4 bytes with signed-byte saturation (I2IP): byte i = sat_s8(v_i)
+    auto pack4_sat_s8 = [](int a, int b, int c, int d) {
+      uint32_t hi, out;
+      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+      asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(b), "r"(a), "r"(hi));
+      return out;
     };
     // pack 4 clamped values into 4 bytes
     auto pack4 = [](int a, int b, int c, int d) { return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410); };
@@ -694,10 +712,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
                   dr = __hiloint2double(0x43300000, r[k] ^ 0x80000000) - c2.x;
                   mr = c2.y;
                 } else {
-                  dr = (RES_ES == 2) ? (__hiloint2double(0x43300000, r[k]) - kOffU) : (__hiloint2double(0x43300000, r[k] ^ 0x80000000) - kOffS);
+                  dr = (RES_ES == 2) ? __hiloint2double(0x43300000, r[k]) : (__hiloint2double(0x43300000, r[k] ^ 0x80000000) - kOffS);
                   mr = (EPI == TC_EPI_RES22) ? res_M : m1[jj + k];
                 }
-                const double qr = __fma_rn(dr, mr, kMagic);
+                const double qr = __fma_rn(dr, mr, (!DUAL && RES_ES == 2) ? res_C : kMagic);
                 const int vr = __double2loint(qr);
                 const int sum = v + vr;
                 if constexpr (WIDE) {
@@ -710,25 +728,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
               if (low_bits) {
                 int q[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {                                 // y >= 0: unsigned conversion, no sign fix-up
-                  const double dl = __hiloint2double(0x43300000, y[k]) - kOffU;
-                  q[k] = clampi(__double2loint(__fma_rn(dl, low_M, kMagic)), q_lo, q_hi);
-                }
-                if (low_bits == 8) {
-                  lw[h * 2 + 0] = pack4(q[0], q[1], q[2], q[3]);
-                  lw[h * 2 + 1] = pack4(q[4], q[5], q[6], q[7]);
+                for (int k = 0; k < 8; ++k)                                   // y >= 0: unsigned conversion, no sign fix-up
+                  q[k] = __double2loint(__fma_rn(__hiloint2double(0x43300000, y[k]), low_M, low_C));
+                if (sat8) {
+                  lw[h * 2 + 0] = pack4_sat_s8(q[0], q[1], q[2], q[3]);
+                  lw[h * 2 + 1] = pack4_sat_s8(q[4], q[5], q[6], q[7]);
                 } else {
-                  lw[h] = pack_nibbles8(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7]));
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) q[k] = clampi(q[k], q_lo, q_hi);
+                  if (low_bits == 8) {
+                    lw[h * 2 + 0] = pack4(q[0], q[1], q[2], q[3]);
+                    lw[h * 2 + 1] = pack4(q[4], q[5], q[6], q[7]);
+                  } else {
+                    lw[h] = pack_nibbles8(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7]));
+                  }
                 }
               }
               if constexpr (Y_ES == 2) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) ymax = max(ymax, y[k]);
                 uint4 o;
-                o.x = __byte_perm(min(y[0], 65535), min(y[1], 65535), 0x5410);
-                o.y = __byte_perm(min(y[2], 65535), min(y[3], 65535), 0x5410);
-                o.z = __byte_perm(min(y[4], 65535), min(y[5], 65535), 0x5410);
-                o.w = __byte_perm(min(y[6], 65535), min(y[7], 65535), 0x5410);
+                if (p.sat_pack) {      // one saturating pack per pair (clamps to [0, 65535])
+                  o.x = pack2_sat_u16(y[0], y[1]); o.y = pack2_sat_u16(y[2], y[3]);
+                  o.z = pack2_sat_u16(y[4], y[5]); o.w = pack2_sat_u16(y[6], y[7]);
+                } else {
+                  o.x = __byte_perm(min(y[0], 65535), min(y[1], 65535), 0x5410);
+                  o.y = __byte_perm(min(y[2], 65535), min(y[3], 65535), 0x5410);
+                  o.z = __byte_perm(min(y[4], 65535), min(y[5], 65535), 0x5410);
+                  o.w = __byte_perm(min(y[6], 65535), min(y[7], 65535), 0x5410);
+                }
                 if constexpr (S::TMA_IO) *reinterpret_cast<uint4*>(yslice + tma_tile_off(RB, lane, (cb + jj) >> 3)) = o;
                 else *reinterpret_cast<uint4*>(myy + (cb + jj) * 2) = o;
               } else {

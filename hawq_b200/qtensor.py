@@ -19,7 +19,7 @@ import os
 import torch
 
 from . import ops, quant_math as qmath
-from ._lib import EPI_DEQUANT_F32, EPI_RAW_I32, EPI_REQUANT, EPI_RESIDUAL, EP_RATIOS_LE_ONE
+from ._lib import EPI_DEQUANT_F32, EPI_RAW_I32, EPI_REQUANT, EPI_RESIDUAL, EP_RATIOS_LE_ONE, ERR_UNSUPPORTED, HawqError
 
 
 class EngineConfig:
@@ -390,7 +390,13 @@ def _launch_residual(r, low_act, device):
         _, hh, ww, _, _ = _conv_out_hw(conv, ent)
         d1 = ops.conv_desc(nb, hh, ww, ent["cin"], ent["cout"], 1, 1, 1, 0, conv.src.bits, 1)
         d2 = ops.conv_desc(nb2, hh2, ww2, dual["cin"], dual["cout"], 1, 1, dual["stride"], 0, ident.src.bits, 1)
-        ops.conv2d_dual(conv.src.data, d1, ep, ent["w"], chan, d2, ident.src.data, dual["w"], res_chan, out=y, out_low=low)
+        try:
+            ops.conv2d_dual(conv.src.data, d1, ep, ent["w"], chan, d2, ident.src.data, dual["w"], res_chan, out=y, out_low=low)
+        except HawqError as err:
+            if err.code != ERR_UNSUPPORTED:
+                raise
+            res, _ = _conv_raw(ident, device)          # the library declined this combination: two launches, same results
+            _launch_conv(conv, ent, ep, chan, device, out=y, out_low=low, res=res, res_chan=res_chan)
     else:
         _launch_conv(conv, ent, ep, chan, device, out=y, out_low=low, res=res, res_chan=res_chan)
     r.shape = (nb, ent["cout"], ho, wo)
