@@ -109,10 +109,28 @@ static int set_tc_attr() {
   return rc;
 }
 
+// conv_tc launches carry the programmatic-stream-serialization attribute (HAWQ_B200_PDL != 0): the kernel's prologue may
+// start while the previous kernel of the stream drains; the kernel itself waits (griddepcontrol.wait) before touching memory
+template <int BN, int EPI, bool WIDE, bool A4>
+static void launch_tc3(const ConvParams& p, const TcMaps& maps, int grid, cudaStream_t st) {
+  static const bool pdl = [] { const char* e = getenv("HAWQ_B200_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = TcSmem<BN, EPI, A4>::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, EPI, WIDE, A4>, p, maps);   // errors surface through launch_check()
+}
 template <int EPI, bool WIDE, bool A4>
 static void launch_tc2(const ConvParams& p, const TcMaps& maps, bool bn128, int grid, cudaStream_t st) {
-  if (bn128) conv_tc_kernel<128, EPI, WIDE, A4><<<grid, TC_THREADS, TcSmem<128, EPI, A4>::TOTAL, st>>>(p, maps);
-  else conv_tc_kernel<64, EPI, WIDE, A4><<<grid, TC_THREADS, TcSmem<64, EPI, A4>::TOTAL, st>>>(p, maps);
+  if (bn128) launch_tc3<128, EPI, WIDE, A4>(p, maps, grid, st);
+  else launch_tc3<64, EPI, WIDE, A4>(p, maps, grid, st);
 }
 template <int EPI>
 static void launch_tc(const ConvParams& p, const TcMaps& maps, bool bn128, bool ratios_wide, bool a4, int grid, cudaStream_t st) {

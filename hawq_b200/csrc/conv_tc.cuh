@@ -276,6 +276,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Programmatic dependent launch: everything above touched only shared memory / TMEM / kernel parameters, so (when launched
+  // with the programmatic-serialization attribute) it overlaps the tail of the previous kernel in the stream.  From here on
+  // global memory is read and written: wait until the preceding grid has completed and flushed.  Both are no-ops otherwise.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   if (warp < TC_PRODUCER_WARPS) {
     // =============================================================================== producers (128 threads)
     // Coalesced gather: consecutive lanes cover one row's bytes (4 lanes x 16 B = 64 B int8 row, 2 lanes x 16 B = packed
