@@ -182,6 +182,37 @@ def test_conv_residual_wide_ratios_on_tensor_cores(geom):
     ops.reset_status(0)
 
 
+WS_GEOMS = [
+    # N, H, W, Cin, Cout, k, stride, pad : REQUANT with re-tiled weights (w_layout 1), more tiles than SMs
+    (7, 56, 56, 64, 64, 3, 1, 1),      # patch mode, 172 tiles: several tiles per CTA, one channel block
+    (4, 49, 49, 128, 128, 3, 1, 1),    # K = 1152, 152 tiles
+    (3, 57, 57, 256, 256, 1, 1, 0),    # 1x1 stride 1 (TMA-fed int8 / gather 4-bit), 154 tiles, 2 channel blocks
+    (2, 31, 31, 128, 128, 1, 2, 0),    # strided 1x1: gather mode
+    (2, 30, 30, 64, 192, 3, 2, 1),     # strided 3x3: gather mode, 3 narrow channel blocks
+    (1, 9, 9, 64, 64, 1, 1, 0),        # single k-tile, single ragged tile
+]
+
+
+@pytest.mark.parametrize("a_bits", [8, 4])
+@pytest.mark.parametrize("geom", WS_GEOMS)
+def test_conv_requant_retiled_weights_many_tiles(geom, a_bits):
+    n, h, w, cin, cout, k, s, p = geom
+    r = rng(9001 + sum(v * (i + 2) for i, v in enumerate(geom)) + a_bits)
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    x = rand_act(r, n * h * w * cin, a_bits)
+    wt = torch.from_numpy(r.randint(-128, 128, size=(cout, k, k, cin)).astype(np.int8))
+    if a_bits == 4:
+        ops.permute_weights_for_i4(wt)
+    chan = make_chan(r, cout, ratio_lo=2e-5, ratio_hi=2e-3)
+    wg = ops.upload_weights(wt, DEV)
+    d = ops.conv_desc(n, h, w, cin, cout, k, k, s, p, a_bits, 1)
+    for out_bits, clamp, relu in [(8, (-128, 127), 1), (4, (0, 15), 1), (8, (-127, 127), 0)]:
+        ep = ops.epilogue(EPI_REQUANT, relu=relu, out_bits=out_bits, clamp=clamp, flags=TC_FLAG)
+        (c,), (g,) = run_both("conv2d", dict(x=x, desc=d, ep=ep, w=wt, chan=chan, out=out_buf(n * ho * wo * cout, out_bits)), ["out"],
+                              gpu_overrides=dict(w=wg))
+        assert torch.equal(c, g), (geom, a_bits, out_bits, relu)
+
+
 DUAL_GEOMS = [
     # N, Ho, Wo, Cin (last conv), Cin2 (identity conv), Cout, identity stride
     (2, 7, 7, 64, 64, 256, 1),         # ResNet-50 stage-1 shape: M = 98 (< one tile), 2 column tiles of 128
