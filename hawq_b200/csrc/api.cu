@@ -174,6 +174,7 @@ int hawq_create(int device, hawq_handle** out) {
   if ((rc = set_tc_attr<TC_EPI_REQ>()) || (rc = set_tc_attr<TC_EPI_RAW>()) || (rc = set_tc_attr<TC_EPI_RES22>()) ||
       (rc = set_tc_attr<TC_EPI_RES44>()) || (rc = set_tc_attr<TC_EPI_RES42>()) || (rc = set_tc_attr<TC_EPI_DUAL>()))
     return rc;
+  CUDA_TRY(cudaFuncSetAttribute(linear_dp4a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, linear_smem_bytes(LIN_MAX_K)));
   if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
       (rc = set_conv_attr<64, true>()))
     return rc;
@@ -451,6 +452,13 @@ int hawq_conv2d_i4(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_
 int hawq_linear_i8(hawq_handle* h, int32_t N, int32_t K, int32_t Cout, int32_t Cout_pad, const int8_t* x,
                    const int8_t* w, const hawq_chan* chan, const float* fscale, float* out, void* stream) {
   if (Cout < 1 || Cout > Cout_pad) return fail(HAWQ_ERR_BAD_ARG, "hawq_linear_i8: bad Cout/Cout_pad");
+  if (!h || !x || !w || !chan || !fscale || !out || N < 1 || K < 1) return fail(HAWQ_ERR_BAD_ARG, "hawq_linear_i8: null argument or empty shape");
+  static const bool dp4a_enabled = [] { const char* e = getenv("HAWQ_B200_LINEAR_DP4A"); return !(e && e[0] == '0'); }();
+  if (dp4a_enabled && K % LIN_SLAB == 0 && K <= LIN_MAX_K && Cout_pad % LIN_CH == 0 && N <= 65535 * LIN_ROWS) {
+    const dim3 grid((unsigned)(Cout_pad / LIN_CH), (unsigned)((N + LIN_ROWS - 1) / LIN_ROWS), 1);
+    linear_dp4a_kernel<<<grid, 256, linear_smem_bytes(K), (cudaStream_t)stream>>>(x, w, chan, fscale, out, N, K, Cout);
+    return launch_check("linear_dp4a");
+  }
   hawq_conv_desc d;
   memset(&d, 0, sizeof(d));
   d.N = N; d.H = 1; d.W = 1; d.Cin = K; d.Cout = Cout_pad; d.kh = 1; d.kw = 1; d.stride = 1; d.pad = 0; d.a_bits = 8;

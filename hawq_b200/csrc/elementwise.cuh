@@ -175,6 +175,70 @@ __global__ void __launch_bounds__(256) avgpool_requant_kernel(const void* __rest
   }
 }
 
+// QuantLinear tail (quant_modules.py:79-130): out[n][c] = float(sat32(x[n,:] . w[c,:] + bias[c])) * fscale[c].
+// A batch-rows x K x 1000 GEMM is too small for 128 x 128 tensor-core tiles (8 CTAs on 148 SMs), so this kernel spreads
+// the channels over the chip instead: one CTA per 8 output channels (their weights sit in shared memory and are read as
+// warp-wide broadcasts), one thread per (row, 4-channel group), x staged through shared memory in 128-byte slabs
+// (coalesced cp.async, double buffered, rows padded to 144 B so that row-per-lane 16-byte reads are conflict-free), dp4a.
+constexpr int LIN_CH = 8, LIN_ROWS = 128, LIN_SLAB = 128, LIN_PITCH = LIN_SLAB + 16;
+constexpr int LIN_MAX_K = 8192;
+inline int linear_smem_bytes(int K) { return LIN_CH * K + 2 * LIN_ROWS * LIN_PITCH; }
+
+__global__ void __launch_bounds__(256) linear_dp4a_kernel(const int8_t* __restrict__ x, const int8_t* __restrict__ w,
+                                                          const hawq_chan* __restrict__ chan, const float* __restrict__ fscale,
+                                                          float* __restrict__ out, int N, int K, int Cout) {
+  extern __shared__ __align__(16) uint8_t lin_smem[];
+  uint8_t* sW = lin_smem;                       // [LIN_CH][K]
+  uint8_t* sX = lin_smem + LIN_CH * K;          // [2][LIN_ROWS][LIN_PITCH]
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.x * LIN_CH;
+  const int row0 = blockIdx.y * LIN_ROWS;
+  const int row = tid & (LIN_ROWS - 1), cg = tid >> 7;     // a warp shares cg: weight reads are broadcasts
+  const int slabs = K / LIN_SLAB;
+
+  auto load_slab = [&](int s, int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int id = tid + i * 256;
+      const int r = id >> 3, col = id & 7;
+      const bool v = row0 + r < N;
+      const int8_t* src = v ? x + (size_t)(row0 + r) * K + s * LIN_SLAB + col * 16 : x;
+      cp_async_16((uint32_t)__cvta_generic_to_shared(sX + (buf * LIN_ROWS + r) * LIN_PITCH + col * 16), src, v ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+  load_slab(0, 0);
+  for (int i = tid; i < LIN_CH * K / 16; i += 256)        // the 8 weight rows are contiguous in global memory
+    reinterpret_cast<int4*>(sW)[i] = reinterpret_cast<const int4*>(w + (size_t)c0 * K)[i];
+
+  int acc[4] = {0, 0, 0, 0};
+  for (int s = 0; s < slabs; ++s) {
+    if (s + 1 < slabs) { load_slab(s + 1, (s + 1) & 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const uint8_t* xr = sX + ((s & 1) * LIN_ROWS + row) * LIN_PITCH;
+#pragma unroll
+    for (int col = 0; col < 8; ++col) {
+      const int4 xv = *reinterpret_cast<const int4*>(xr + col * 16);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const int4 wv = *reinterpret_cast<const int4*>(sW + (size_t)(cg * 4 + ch) * K + s * LIN_SLAB + col * 16);
+        acc[ch] = __dp4a(xv.x, wv.x, acc[ch]);
+        acc[ch] = __dp4a(xv.y, wv.y, acc[ch]);
+        acc[ch] = __dp4a(xv.z, wv.z, acc[ch]);
+        acc[ch] = __dp4a(xv.w, wv.w, acc[ch]);
+      }
+    }
+    __syncthreads();                                       // the buffer is refilled two iterations later
+  }
+  if (row0 + row < N) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int c = c0 + cg * 4 + ch;
+      if (c < Cout) out[(size_t)(row0 + row) * Cout + c] = __int2float_rn(sat_add(acc[ch], chan[c].bias)) * fscale[c];
+    }
+  }
+}
+
 // integer NHWC -> fp32 NCHW value q * scale (fp32 multiply, as quant_modules.py:303).  One thread per output element.
 __global__ void __launch_bounds__(256) dequant_f32_kernel(const void* __restrict__ x, int N, int H, int W, int C,
                                                           int x_bits, int x_signed, float scale,

@@ -310,6 +310,20 @@ def test_conv_raw_and_dequant():
     assert torch.equal(c, g)
 
 
+@pytest.mark.parametrize("shape", [(130, 2048, 1000, 1024), (128, 512, 10, 64), (3, 192, 100, 128), (1, 64, 64, 64)])
+def test_linear_shapes(shape):
+    """QuantLinear tail over both implementations: dp4a kernel (K % 128 == 0) and the generic convolution path (other K)."""
+    nb, kk, co, cp = shape
+    r = rng(31 + nb + kk + co)
+    xl = rand_act(r, nb * kk, 8)
+    wl = torch.zeros((cp, kk), dtype=torch.int8)
+    wl[:co] = torch.from_numpy(r.randint(-128, 128, size=(co, kk)).astype(np.int8))
+    chl = make_chan(r, cp, bias_mag=2 ** 20)
+    fs = torch.from_numpy(r.uniform(1e-5, 1e-3, size=cp).astype(np.float32))
+    (c,), (g,) = run_both("linear", dict(x=xl, w=wl, chan=chl, fscale=fs, out=torch.zeros((nb, co)), n=nb, k=kk, cout=co, cout_pad=cp), ["out"])
+    assert torch.equal(c, g), shape
+
+
 @pytest.mark.parametrize("shape", [(2, 32, 32), (1, 224, 224), (3, 30, 46)])
 def test_stem_and_pool(shape):
     n, h, w = shape
