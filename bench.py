@@ -348,9 +348,21 @@ def roofline_leg(hb, ops, q, dev_pool, a):
     top = max(fam, key=lambda k: fam[k]["ms"])
     t = fam[top]
     achieved = t["bytes"] / (t["ms"] / 1e3) / 1e9
+    # measured DRAM traffic of the same kernel family: not measurable live (needs ncu); taken from the committed summary of
+    # the ncu pass over this very command (tools/summarize_ncu.py -> profiles/ncu_traffic.json), null if there is none
+    traffic = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f).get("%s:%s:%d" % (a.arch, a.scheme, a.batch))
+        if ent and top == "conv_tc_kernel":
+            traffic = ent["traffic_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        traffic = None
     roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % which if which == "measured" else "fallback 6650 GB/s",
-            "traffic": None, "launches_per_step": t["launches"], "share_of_step": t["ms"] / total_ms,
+            "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)" if traffic else None,
+            "algorithmic_bytes_per_launch": t["bytes"] / t["launches"],
+            "launches_per_step": t["launches"], "share_of_step": t["ms"] / total_ms,
             "algorithmic_bytes_per_step": t["bytes"], "avg_launch_ms": t["ms"] / t["launches"],
             "tensor_tops": 2 * t["macs"] / (t["ms"] / 1e3) / 1e12,
             "note": "all %d %s launches of one step (the tcgen05 implicit-GEMM template behind hawq_conv2d and hawq_conv2d_dual): sum of algorithmic bytes / sum of CUDA-event durations (eager pass on the launch stream)" % (t["launches"], top)}
