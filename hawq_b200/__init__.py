@@ -16,6 +16,8 @@ from .q_resnet import (Q_ResBlockBn, Q_ResNet18, Q_ResNet50, Q_ResNet101, Q_ResU
 from .bit_config import bit_config_dict, get_bit_config, stamp_bit_config  # noqa: F401
 from .engine import CompiledModel, all_gather_logits, compile_model, shard_range  # noqa: F401
 from .qtensor import IntActivation  # noqa: F401
+from .checkpoint import (apply_integer_checkpoint, export_tvm_params, load_quantized_checkpoint,  # noqa: F401
+                         quantized_checkpoint_dict, save_quantized_checkpoint, save_tvm_params)
 
 __version__ = "0.1.0"
 

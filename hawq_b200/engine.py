@@ -61,6 +61,10 @@ class CompiledModel:
             out = self._forward(bits)                  # warm-up: builds all parameter caches
             self.launches[key] = ops.launch_count - before
             self._forward(bits)
+        # keep every module's plan (device-resident weights / per-channel parameters) alive for as long as graphs captured
+        # here may replay, even if the modules drop or rebuild theirs (unfix(), load_state_dict)
+        self._plans = getattr(self, "_plans", [])
+        self._plans.append([m.__dict__["_hawq_cache"] for m in self.model.modules() if "_hawq_cache" in m.__dict__])
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self.bits_of = getattr(self, 'bits_of', {})

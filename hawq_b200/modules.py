@@ -32,6 +32,11 @@ def _check_mode(mode):
         raise ValueError("unknown quant mode: {}".format(mode))
 
 
+def _drop_plan(module):
+    """unfix(): the device-resident integer plan is rebuilt on the next frozen forward (SURVEY.md 8(b) lifecycle)."""
+    module.__dict__.pop("_hawq_cache", None)
+
+
 def _frozen_dispatch(module, name, *args, **kw):
     from . import qtensor
     return getattr(qtensor, name)(module, *args, **kw)
@@ -69,9 +74,22 @@ class QuantAct(Module):
         self.running_stat = True
         self.fix_flag = False
 
+    def load_frozen_scale(self, scale):
+        """Use a stored ``act_scaling_factor`` (quantized_checkpoint.pth.tar) instead of the scale implied by x_min / x_max;
+        ``None`` returns to the range buffers."""
+        if scale is None:
+            self.__dict__.pop("_scale_override", None)
+            return
+        sf = scale.detach().to(self.x_min.device, torch.float32).reshape(-1)[:1].clone()
+        self.__dict__["_scale_override"] = sf
+        self.act_scaling_factor = sf.clone()
+
     def current_scale(self):
-        """Scale implied by the range buffers (quant_modules.py:262-270)."""
+        """Scale implied by the range buffers (quant_modules.py:262-270), or the one loaded by ``load_frozen_scale``."""
         _check_mode(self.quant_mode)
+        ov = self.__dict__.get("_scale_override")
+        if ov is not None:
+            return ov
         if self.quant_mode == "symmetric":
             return qmath.symmetric_scale(self.activation_bit, self.x_min, self.x_max, False)
         return qmath.asymmetric_scale(self.activation_bit, self.x_min, self.x_max)
@@ -131,12 +149,34 @@ class QuantAct(Module):
 
 
 class _WeightQuantMixin:
+    def load_frozen_integers(self, w_sf, w_int, b_int=None):
+        """Use stored integers (``weight_integer`` in the float weights' layout, per-channel scale, optional 32-bit
+        ``bias_integer``) instead of deriving them from the float parameters; ``w_sf=None`` returns to the float parameters."""
+        if w_sf is None:
+            self.__dict__.pop("_frozen_integers", None)
+            return
+        ref = self.conv.weight if hasattr(self, "conv") else self.weight
+        w_int = w_int.detach().to(ref.device, torch.float32).reshape(ref.shape).clone()
+        w_sf = w_sf.detach().to(ref.device, torch.float32).reshape(-1).clone()
+        if w_sf.numel() not in (1, ref.shape[0]):
+            raise ValueError("scale has %d entries for %d output channels" % (w_sf.numel(), ref.shape[0]))
+        lim = 2 ** (self.weight_bit - 1)
+        if float(w_int.min()) < -lim or float(w_int.max()) > lim - 1:
+            raise ValueError("weight_integer does not fit %d bits" % self.weight_bit)
+        if b_int is not None:
+            b_int = b_int.detach().to(ref.device, torch.float32).reshape(-1).clone()
+        self.__dict__["_frozen_integers"] = (w_sf, w_int, b_int)
+
     def _weight_params(self, w, bias, pre_act_sf, percentile):
         """Per-channel (or per-tensor) symmetric integer weights + 32-bit integer bias
         (quant_modules.py:451-484 / 97-118 / 689-722)."""
         if self.quant_mode != "symmetric":
             _check_mode(self.quant_mode)
             raise Exception('For weight, we only support symmetric quantization.')
+        ov = self.__dict__.get("_frozen_integers")
+        if ov is not None:                       # integers loaded from a quantized checkpoint: they are the plan
+            w_sf, w_int, b_int = ov
+            return w_sf, w_int, b_int, w_sf.view(1, -1) * pre_act_sf.view(1, -1)
         w2 = w.data.contiguous().view(w.shape[0], -1)
         if self.per_channel:
             lo, hi = qmath.per_channel_minmax(w2, percentile)
@@ -190,6 +230,7 @@ class QuantBnConv2d(Module, _WeightQuantMixin):
     def unfix(self):
         self.fix_flag = False
         self.fix_BN = self.training_BN_mode
+        _drop_plan(self)
 
     def integer_params(self, pre_act_scaling_factor):
         """(w_sf[C], weight_integer OIHW, bias_integer[C], bias_sf[1,C]) of the folded-BN branch; also refreshes the
@@ -268,6 +309,7 @@ class QuantConv2d(Module, _WeightQuantMixin):
 
     def unfix(self):
         self.fix_flag = False
+        _drop_plan(self)
 
     def integer_params(self, pre_act_scaling_factor):
         w_sf, w_int, b_int, bias_sf = self._weight_params(self.weight, self.bias, pre_act_scaling_factor,
@@ -320,6 +362,7 @@ class QuantLinear(Module, _WeightQuantMixin):
 
     def unfix(self):
         self.fix_flag = False
+        _drop_plan(self)
 
     def integer_params(self, prev_act_scaling_factor):
         w_sf, w_int, b_int, bias_sf = self._weight_params(self.weight, self.bias, prev_act_scaling_factor, 0)

@@ -153,7 +153,7 @@ def _act_clamp(act):
 def _frozen_scale(act):
     """Scale of a frozen QuantAct, CPU fp32 [1]; refreshes the act_scaling_factor buffer like the reference forward."""
     c = act.__dict__.setdefault("_hawq_cache", {})
-    key = ("scale", _key(act.x_min), _key(act.x_max), act.activation_bit, act.quant_mode)
+    key = ("scale", _key(act.x_min), _key(act.x_max), act.activation_bit, act.quant_mode, id(act.__dict__.get("_scale_override")))
     if c.get("scale_key") != key:
         sf = act.current_scale().detach().to("cpu", torch.float32).reshape(1)
         c["scale_key"], c["scale"] = key, sf
@@ -183,13 +183,32 @@ def _ones():
 
 
 # ------------------------------------------------------------------------------------------------ conv params
+_OWN_BUFFERS = ("weight_integer", "bias_integer", "convbn_scaling_factor", "conv_scaling_factor", "fc_scaling_factor")
+
+
+def _param_versions(mod):
+    """In-place modification counters of every float parameter / statistic the integer plan of `mod` derives from:
+    ``load_state_dict`` and optimizer steps write in place, so a changed tuple invalidates the cached plan (the reference
+    recomputes its integers on every forward, quant_modules.py:440-484; SURVEY.md 8(b) lifecycle row)."""
+    vs = []
+    for name, t in list(mod.named_parameters()) + list(mod.named_buffers()):
+        if name.rsplit(".", 1)[-1] in _OWN_BUFFERS or "num_batches_tracked" in name:
+            continue
+        vs.append((id(t), t._version))
+    vs.append(id(mod.__dict__.get("_frozen_integers")))      # integers installed from a quantized checkpoint
+    return tuple(vs)
+
+
+
 def _conv_cache(mod, a_sf, a_bits, device):
     """Device-resident integer parameters of a frozen conv module for input scale a_sf / input width a_bits."""
     c = mod.__dict__.setdefault("_hawq_cache", {})
-    key = (_key(a_sf), a_bits, str(device), mod.weight_bit, mod.per_channel, mod.bias_bit, mod.quantize_bias)
+    key = (_key(a_sf), a_bits, str(device), mod.weight_bit, mod.per_channel, mod.bias_bit, mod.quantize_bias, _param_versions(mod))
     ent = c.get(key)
     if ent is not None:
         return ent
+    if c:              # a different scale / bit width / parameter version: start a new plan.  The old dict is not cleared in
+        c = mod.__dict__["_hawq_cache"] = {}     # place: a CompiledModel may still replay graphs that read its buffers
     with torch.no_grad():
         conv = mod.conv
         src_dev = conv.weight.device
@@ -553,9 +572,11 @@ def linear_forward(mod, x, a_sf):
         raise NotImplementedError("QuantLinear input must be signed int8")
     dev = x.device
     c = mod.__dict__.setdefault("_hawq_cache", {})
-    key = (_key(a_sf), str(dev), mod.weight_bit, mod.per_channel)
+    key = (_key(a_sf), str(dev), mod.weight_bit, mod.per_channel, _param_versions(mod))
     ent = c.get(key)
     if ent is None:
+        if c:
+            c = mod.__dict__["_hawq_cache"] = {}
         with torch.no_grad():
             w_sf, w_int, b_int, bias_sf = mod.integer_params(a_sf.to(mod.weight.device))
             cout, k = w_int.shape
