@@ -517,6 +517,21 @@ int hawq_quantize_input_f32(hawq_handle* h, int32_t N, int32_t C, int32_t H, int
   return launch_check("quantize_input");
 }
 
+int hawq_quantize_input_u8(hawq_handle* h, int32_t N, int32_t H, int32_t W, const uint8_t* x, const float* mean3,
+                           const float* std3, float scale, int32_t lo, int32_t hi, int8_t* out, void* stream) {
+  if (!h || !x || !out || !mean3 || !std3) return fail(HAWQ_ERR_BAD_ARG, "hawq_quantize_input_u8: null argument");
+  if (N < 1 || H < 1 || W < 1) return fail(HAWQ_ERR_BAD_ARG, "hawq_quantize_input_u8: empty shape");
+  if (!(scale > 0.f)) return fail(HAWQ_ERR_BAD_ARG, "hawq_quantize_input_u8: scale must be > 0");
+  if (lo < -128 || hi > 127 || lo > hi) return fail(HAWQ_ERR_BAD_ARG, "hawq_quantize_input_u8: clamp must fit int8");
+  for (int c = 0; c < 3; ++c)
+    if (!(std3[c] > 0.f)) return fail(HAWQ_ERR_BAD_ARG, "hawq_quantize_input_u8: std must be > 0");
+  const float inv = 1.0f / scale;  // fp32 division, as `1. / scale` in linear_quantize (quant_utils.py:97)
+  const long long n_bytes = (long long)N * H * W * 3;
+  quantize_input_u8_kernel<<<grid_for(n_bytes / 4 + 1, h->sm_count), 256, 0, (cudaStream_t)stream>>>(
+      x, n_bytes, 3, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], inv, lo, hi, out);
+  return launch_check("quantize_input_u8");
+}
+
 int hawq_requant(hawq_handle* h, int64_t rows, int32_t C, int32_t x_bits, const void* x, const hawq_chan* chan,
                  int32_t chan_stride, int32_t relu, int32_t out_bits, int32_t lo, int32_t hi, void* out, void* stream) {
   if (!h || !x || !chan || !out) return fail(HAWQ_ERR_BAD_ARG, "hawq_requant: null argument");

@@ -1,21 +1,27 @@
 // Persistent warp-specialised implicit-GEMM convolution on 5th-gen tensor cores (tcgen05.mma kind::i8, TMEM
-// accumulators) with the HAWQ epilogues fused.  One CTA per SM loops over 128 x BN output tiles.
+// accumulators) with the HAWQ epilogues fused.  One CTA per SM loops over 128 x BN output tiles (m fastest).
 //
-//   warps 0-3   producers: gather the A (im2col rows, zero-filled halo) and B (weights) k-tiles with 16-byte cp.async
-//               into a STAGES-deep shared-memory ring laid out in the UMMA canonical K-major SWIZZLE_64B format
-//               (rows of 64 int8, 16-byte chunk index XOR (row >> 1) & 3), then fence.proxy.async + mbarrier arrive;
-//   warp  4     allocates TMEM, one elected lane issues tcgen05.mma (M = 128, N = BN, K = 32; two per k-tile) into one
-//               of two TMEM accumulator buffers, tcgen05.commit releases smem stages / publishes the accumulator;
-//   warps 5-12  epilogue: tcgen05.ld the accumulator (thread = output row, 32 consecutive channels per load),
-//               exact FP64-FMA dyadic requantisation, residual add, ReLU, low-bit copy; every warp owns a private
-//               shared-memory slice (residual tile in, outputs staged in place) so only __syncwarp is needed, and all
-//               global traffic is full-line coalesced.
+//   warps 0-3   producers: fill a STAGES-deep shared-memory ring of A (128 x 64 B) and B (BN x 64 B) k-tiles in the UMMA
+//               canonical K-major SWIZZLE_64B layout (16-byte chunk index XOR (row >> 1) & 3).
+//                 B: one linear cp.async.bulk per k-tile from the re-tiled weight copy (or a TMA box of plain OHWI weights);
+//                 A: TMA boxes (1x1 stride-1 int8 layers) | 3x3 stride-1 "patch mode": one TMA box per (tile, Cin chunk)
+//                    brings the pixel range of all nine taps, the taps are copied shared -> shared | coalesced cp.async
+//                    gather with hardware-signalled mbarrier arrival (strided layers, dual mode);
+//                 packed 4-bit activations are expanded to int8 here (A4);
+//   warp  4     allocates TMEM; one lane issues tcgen05.mma (M = 128, N = BN, K = 32; two per k-tile) into one of two TMEM
+//               accumulator buffers (dual mode: two accumulators per buffer), tcgen05.commit releases smem stages / publishes
+//               the accumulator;
+//   warps 5-12  epilogue: tcgen05.ld the accumulator (thread = output row, 32 consecutive channels per load), exact FP64-FMA
+//               dyadic requantisation, residual add, ReLU, low-bit copy.  REQUANT / int32 variants stage outputs in a private
+//               padded slice and copy out coalesced; the uint16-stream variants (RES22, DUAL) read the residual tile and write
+//               the new stream + low-bit tile as swizzled TMA boxes.
 //   While the epilogue of tile i runs, the producers and the MMA warp are already working on tile i+1.
 //
-// Supported: a_bits == 8 (signed), epilogue REQUANT -> 4/8 bit, RESIDUAL, RAW_I32, all dyadic ratios <= 1 (promised by
-// the caller through slow_scalar == 0 / HAWQ_EP_RATIOS_LE_ONE and re-checked here: a violation raises
-// HAWQ_FLAG_BAD_RATIO in the status word instead of producing wrong numbers).  Everything else uses conv_igemm.cuh.
-// Every mbarrier wait is bounded: a protocol bug traps (launch failure) instead of hanging the GPU.
+// Supported: a_bits 8 (signed) / 4 (unsigned, packed), epilogues REQUANT -> 4/8 bit, RESIDUAL (relu), RAW_I32, DUAL; dyadic
+// ratios <= 1, or <= 2^20 with the WIDE overflow checks (promised by the caller through HAWQ_EP_RATIOS_* and re-checked here:
+// a violation raises HAWQ_FLAG_BAD_RATIO / HAWQ_FLAG_REQUANT_OVERFLOW in the status word instead of producing wrong numbers).
+// Everything else uses conv_igemm.cuh.  Every mbarrier wait is bounded: a protocol bug traps (launch failure) instead of
+// hanging the GPU.
 #pragma once
 #include <cuda.h>
 
@@ -131,15 +137,6 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
-      "selp.u32 %0, 1, 0, px;\n\t}"
-      : "=r"(pred));
-  return pred;
-}
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
@@ -186,10 +183,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// asynchronous row store smem -> global through the bulk-copy engine (bytes % 16 == 0, both 16-byte aligned)
-__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
-}
+// bulk-copy (TMA) store groups
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

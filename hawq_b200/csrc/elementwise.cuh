@@ -83,6 +83,40 @@ __global__ void __launch_bounds__(256) quantize_input_kernel(const float* __rest
   }
 }
 
+// uint8 image pipeline (tvm_benchmark/test_resnet_accuracy_imagenet.py:62-75,82-93): ToTensor (u / 255),
+// Normalize ((v - mean_c) / std_c) and the QuantAct input branch (clamp(rint((1/scale) * x))) in one pass, uint8 NHWC -> int8 NHWC.
+// Every step is the same single fp32 operation the reference's torch pipeline performs, so the integers are identical; with
+// 256 possible inputs per channel the whole map is a 3 x 256 table built once per block in shared memory.
+__global__ void __launch_bounds__(256) quantize_input_u8_kernel(const uint8_t* __restrict__ x, long long n_bytes, int C,
+                                                                float m0, float m1, float m2, float s0, float s1, float s2,
+                                                                float inv_scale, int lo, int hi, int8_t* __restrict__ out) {
+  __shared__ int8_t lut[3 * 256];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+    const int c = i >> 8, u = i & 255;
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const float v = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.0f), mean), sd);
+    const float q = rintf(__fmul_rn(inv_scale, v));
+    lut[i] = (int8_t)(int)fminf(fmaxf(q, (float)lo), (float)hi);
+  }
+  __syncthreads();
+  const long long words = n_bytes >> 2;
+  for (long long wi = blockIdx.x * (long long)blockDim.x + threadIdx.x; wi < words; wi += (long long)gridDim.x * blockDim.x) {
+    const uint32_t v = reinterpret_cast<const uint32_t*>(x)[wi];
+    int c = (int)((wi * 4) % C);
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o |= (uint32_t)(uint8_t)lut[(c << 8) | ((v >> (8 * j)) & 0xFF)] << (8 * j);
+      c = (c + 1 == C) ? 0 : c + 1;
+    }
+    reinterpret_cast<uint32_t*>(out)[wi] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n_bytes & 3)) {          // tail bytes
+    const long long i = (words << 2) + threadIdx.x;
+    out[i] = lut[((int)(i % C) << 8) | x[i]];
+  }
+}
+
 // case 0 stand-alone: out = clamp(RHE(([relu](x + bias)) * m / 2^e)).
 __global__ void __launch_bounds__(256) requant_kernel(const void* __restrict__ x, long long rows, int C, int x_bits,
                                                       const hawq_chan* __restrict__ chan, int chan_stride, int relu,

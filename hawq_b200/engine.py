@@ -19,15 +19,30 @@ from .modules import freeze_model
 from .qtensor import IntActivation, Node
 
 
-class CompiledModel:
-    """input: int8 NHWC [N,H,W,3] (already quantised with the model's input scale) or fp32 NCHW [N,3,H,W]."""
+IMAGENET_MEAN = (0.485, 0.456, 0.406)      # transforms.Normalize of the reference's loaders (quant_train.py:357-358,
+IMAGENET_STD = (0.229, 0.224, 0.225)       # tvm_benchmark/test_resnet_accuracy_imagenet.py:82-83)
 
-    def __init__(self, model, example, use_cuda_graph=True, residual_bits=16):
+
+class CompiledModel:
+    """input: int8 NHWC [N,H,W,3] (already quantised with the model's input scale), fp32 NCHW [N,3,H,W] (normalised, what the
+    reference's loaders produce), or uint8 NHWC [N,H,W,3] raw pixels (ToTensor + Normalize(mean, std) + input quantisation are
+    then one kernel at the head of the graph; needs ``model.quant_input``)."""
+
+    def __init__(self, model, example, use_cuda_graph=True, residual_bits=16, mean=IMAGENET_MEAN, std=IMAGENET_STD):
         if not example.is_cuda:
             raise RuntimeError("compile_model needs a CUDA example input: the frozen path has no CPU implementation")
         self.model = model
         self.device = example.device
         self.int_input = example.dtype == torch.int8
+        self.u8_input = example.dtype == torch.uint8
+        self.mean, self.std = tuple(mean), tuple(std)
+        if self.u8_input:
+            if example.dim() != 4 or example.shape[-1] != 3:
+                raise ValueError("uint8 input must be NHWC with 3 channels")
+            act = getattr(model, "quant_input", None)
+            if act is None or act.activation_bit != 8 or act.quant_mode != "symmetric":
+                raise NotImplementedError("uint8 input needs an 8-bit symmetric `quant_input` QuantAct at the head of the model")
+            self._q_in = torch.empty(example.numel(), dtype=torch.int8, device=example.device)
         self.static_in = example.clone()
         self.use_graph = use_cuda_graph
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -44,7 +59,12 @@ class CompiledModel:
     def _forward(self, bits):
         qtensor.config.residual_bits = bits
         x = self.static_in
-        if self.int_input:
+        if self.u8_input:
+            act = self.model.quant_input
+            ops.quantize_input_u8(x, self.mean, self.std, float(qtensor._frozen_scale(act)), qtensor._act_clamp(act), self._q_in)
+            n, h, w, c = x.shape
+            x = IntActivation(Node("int", (n, c, h, w), data=self._q_in, bits=8, signed=True), self.device)
+        elif self.int_input:
             n, h, w, c = x.shape
             x = IntActivation(Node("int", (n, c, h, w), data=x.view(-1), bits=8, signed=True), self.device)
         out = self.model(x)
@@ -173,11 +193,12 @@ class CompiledModel:
         return self.launches.get(self.residual_bits, 0)
 
 
-def compile_model(model, example, use_cuda_graph=True, residual_bits=16):
-    """Freeze ``model`` (a QResNet or any graph built from hawq_b200.modules) and compile it for ``example``'s shape."""
+def compile_model(model, example, use_cuda_graph=True, residual_bits=16, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """Freeze ``model`` (a QResNet or any graph built from hawq_b200.modules) and compile it for ``example``'s shape and dtype
+    (int8 NHWC, fp32 NCHW or uint8 NHWC; ``mean`` / ``std`` only matter for uint8 pixels)."""
     freeze_model(model)
     model.eval()
-    return CompiledModel(model, example, use_cuda_graph=use_cuda_graph, residual_bits=residual_bits)
+    return CompiledModel(model, example, use_cuda_graph=use_cuda_graph, residual_bits=residual_bits, mean=mean, std=std)
 
 
 def all_gather_logits(local_logits, group=None):

@@ -198,6 +198,18 @@ def quantize_input(x, scale, clamp, out):
     _count("quantize_input", (0, n * c * hh * ww * 5) if ev is not None else None, ev)
 
 
+def quantize_input_u8(x, mean, std, scale, clamp, out):
+    """uint8 NHWC images -> int8 NHWC network input (ToTensor + Normalize + QuantAct input branch in one kernel)."""
+    n, hh, ww, c = x.shape
+    if c != 3:
+        raise ValueError("quantize_input_u8 expects NHWC images with 3 channels")
+    h, s = _ctx(x)
+    ev = _begin()
+    m3, s3 = (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std])
+    _lib.check(_lib.load().hawq_quantize_input_u8(h, n, hh, ww, _p(x), m3, s3, float(scale), clamp[0], clamp[1], _p(out), s))
+    _count("quantize_input_u8", (0, n * hh * ww * 6) if ev is not None else None, ev)
+
+
 def requant(x, rows, c, x_bits, chan, chan_stride, relu, out_bits, clamp, out):
     h, s = _ctx(x)
     _lib.check(_lib.load().hawq_requant(h, rows, c, x_bits, _p(x), _p(chan), chan_stride, int(relu), out_bits,

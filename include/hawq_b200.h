@@ -177,6 +177,11 @@ int hawq_avgpool_requant(hawq_handle* h, int32_t N, int32_t HW, int32_t C, int32
  * x fp32 NCHW [N,C,H,W] -> int8 NHWC [N,H,W,C]. */
 int hawq_quantize_input_f32(hawq_handle* h, int32_t N, int32_t C, int32_t H, int32_t W, const float* x,
                             float scale, int32_t lo, int32_t hi, int8_t* out, void* stream);
+/* uint8 image entry (tvm_benchmark/test_resnet_accuracy_imagenet.py:62-75 quantize_image after transforms.ToTensor + Normalize
+ * :82-93): x uint8 NHWC [N,H,W,3] -> int8 NHWC, q = clamp(round((1/scale) * ((x / 255 - mean[c]) / std[c]))), every step one fp32
+ * operation as in the torch pipeline.  mean3 / std3 are HOST pointers to three floats (copied at launch). */
+int hawq_quantize_input_u8(hawq_handle* h, int32_t N, int32_t H, int32_t W, const uint8_t* x, const float* mean3,
+                           const float* std3, float scale, int32_t lo, int32_t hi, int8_t* out, void* stream);
 /* fixedpoint_fn case 0 stand-alone (QuantAct after a conv or at unit entry): x [rows,C] (x_bits 16 = uint16 residual,
  * 32 = int32), per-channel chan (bias is added; pass 0) or scalar when chan_stride == 0 (chan[0] used for all). */
 int hawq_requant(hawq_handle* h, int64_t rows, int32_t C, int32_t x_bits, const void* x, const hawq_chan* chan,

@@ -171,6 +171,14 @@ def quantize_input(x, scale, clamp, out):
     encode_into(out, np.clip(q, clamp[0], clamp[1]), 8)
 
 
+def quantize_input_u8(x, mean, std, scale, clamp, out):
+    """ToTensor (u / 255), Normalize ((v - mean) / std), QuantAct input branch: one fp32 operation per step, like torch."""
+    u = x.detach().cpu().numpy().astype(np.float32)                              # NHWC
+    v = (u / np.float32(255.0) - np.asarray(mean, dtype=np.float32)) / np.asarray(std, dtype=np.float32)
+    q = ir.quantize_input(np.ascontiguousarray(v.transpose(0, 3, 1, 2)), np.float32(scale), 8, 'symmetric')
+    encode_into(out, np.clip(q, clamp[0], clamp[1]), 8)
+
+
 def requant(x, rows, c, x_bits, chan, chan_stride, relu, out_bits, clamp, out):
     xa = decode(x, x_bits, x_bits == 32).reshape(rows, c)
     bias, m, e = chan_fields(chan)
@@ -222,7 +230,7 @@ def install_cpu_backend(monkeypatch):
     from hawq_b200 import ops
     status["flags"] = 0
     for name, fn in dict(conv2d=conv2d, conv2d_dual=conv2d_dual, linear=linear, stem_conv=stem_conv, maxpool_requant=maxpool_requant,
-                         avgpool_requant=avgpool_requant, quantize_input=quantize_input, requant=requant,
+                         avgpool_requant=avgpool_requant, quantize_input=quantize_input, quantize_input_u8=quantize_input_u8, requant=requant,
                          add_requant=add_requant, dequant=dequant, pack_i4=pack_i4_op, unpack_i4=unpack_i4_op).items():
         monkeypatch.setattr(ops, name, fn)
     monkeypatch.setattr(ops, "reset_status", lambda idx: status.__setitem__("flags", 0))

@@ -394,6 +394,25 @@ def test_avgpool_quantize_requant_dequant_pack():
     assert torch.equal(packed.cpu(), torch.from_numpy(am.pack_i4(v.numpy()))) and torch.equal(back.cpu(), v)
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 32), (1, 7, 9), (3, 5, 5)])
+def test_quantize_input_u8(shape):
+    """uint8 pixels -> int8 network input: equal to the ABI model AND to the two-step torch pipeline + hawq_quantize_input_f32."""
+    n, h, w = shape
+    r = rng(77 + n * h * w)
+    u8 = torch.from_numpy(r.randint(0, 256, size=(n, h, w, 3)).astype(np.uint8))
+    if n == 2:
+        u8.view(-1)[:768] = torch.arange(256, dtype=torch.uint8).repeat_interleave(3)       # every value in every channel
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    for scale, clamp in [(0.0207, (-128, 127)), (0.005, (-128, 127)), (0.05, (-127, 127))]:
+        (c,), (g,) = run_both("quantize_input_u8", dict(x=u8, mean=mean, std=std, scale=scale, clamp=clamp, out=out_buf(n * h * w * 3, 8)), ["out"])
+        assert torch.equal(c, g), (shape, scale)
+        x = u8.permute(0, 3, 1, 2).to(torch.float32).div(255)
+        x = x.sub(torch.tensor(mean).view(1, 3, 1, 1)).div(torch.tensor(std).view(1, 3, 1, 1))
+        two_step = torch.zeros(n * h * w * 3, dtype=torch.int8, device=DEV)
+        ops.quantize_input(x.contiguous().to(DEV), scale, clamp, two_step)
+        assert torch.equal(two_step.cpu(), g), (shape, scale, "vs torch pipeline")
+
+
 def test_bad_arguments_are_reported():
     x = torch.zeros(64 * 4, dtype=torch.int8, device=DEV)
     w = torch.zeros((64, 1, 1, 48), dtype=torch.int8, device=DEV)

@@ -116,3 +116,29 @@ def test_uint16_overflow_falls_back_exactly():
     got = eng(x.to(DEV))
     assert eng.fallbacks == 1
     assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_compiled_graph_uint8_pixels_equal_the_torch_pipeline():
+    """uint8 NHWC pixels -> fused ToTensor/Normalize/quantise kernel at the head of the graph == the reference's loader pipeline
+    (transforms.ToTensor + Normalize, fp32 NCHW) fed to the same frozen model; and weights reloaded in place invalidate the plan."""
+    from hawq_b200.engine import IMAGENET_MEAN, IMAGENET_STD
+    logits_g, meta = load_net_golden("resnet18", "uniform8")
+    q = _model("resnet18", "uniform8", meta)
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (3, 224, 224, 3), generator=g, dtype=torch.uint8)
+    x = u8.permute(0, 3, 1, 2).to(torch.float32).div(255)                               # transforms.ToTensor
+    x = x.sub(torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)).div(torch.tensor(IMAGENET_STD).view(1, 3, 1, 1))   # Normalize
+    with torch.no_grad():
+        want = q(x.to(DEV)).cpu()
+    eng = hb.compile_model(q, u8.to(DEV))
+    got = eng(u8.to(DEV)).cpu()
+    assert torch.equal(got, want)
+    # eager plan invalidation on the CUDA path: scaling one conv's float weights in place changes the logits, restoring them
+    # restores the logits (load_state_dict writes in place)
+    sd = {k: v.clone() for k, v in q.state_dict().items()}
+    with torch.no_grad():
+        q.stage1.unit1.quant_convbn1.conv.weight.mul_(0.5)
+        changed = q(x.to(DEV)).cpu()
+        assert not torch.equal(changed, want)
+        q.load_state_dict(sd)
+        assert torch.equal(q(x.to(DEV)).cpu(), want)
