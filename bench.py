@@ -290,7 +290,8 @@ def run_ours(a):
                 "config": {"workload": "%s_%s_b%d" % (a.arch, a.scheme, B), "arch": a.arch, "bit_config": a.scheme, "batch_per_gpu": B,
                            "global_batch": B * world, "input": "synthetic int8 NHWC 224x224x3, %d rotating batches" % POOL,
                            "parallelism": "dp%d (batch sharded, logits all-gather)" % world if world > 1 else "single GPU",
-                           "l2": "per-step working set (%.1f GB of activations) exceeds the 126 MB L2; inputs rotate" % (detail["act_bytes"] / 1e9 if detail else 0.0),
+                           "l2": ("per-step working set (%.1f GB of activations) exceeds the 126 MB L2; inputs rotate" % (detail["act_bytes"] / 1e9)) if detail
+                                 else "per-step working set (GBs of activations at batch 128) exceeds the 126 MB L2; inputs rotate",
                            "residual_stream": "uint%d" % a.residual_bits if a.residual_bits == 16 else "int32", "cuda_graph": True,
                            "overflow_flag_seen": bool(flag & 1)},
                 "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(host_pool[0].numel()),
