@@ -232,6 +232,9 @@ def make_net(ns, arch, scheme):
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     ns = rh.load()
+    if len(sys.argv) == 4 and sys.argv[1] == "--net":         # one extra network golden, e.g. --net resnet101 uniform8
+        make_net(ns, sys.argv[2], sys.argv[3])
+        sys.exit(0)
     make_kat_requant(ns)
     make_kat_modules(ns)
     for arch, scheme in NET_CONFIGS:

@@ -29,7 +29,8 @@ def _hook_outputs(q):
 
 
 @pytest.mark.parametrize("arch,scheme,res_bits", [("resnet18", "uniform8", 32), ("resnet18", "uniform4", 16),
-                                                  ("resnet18", "bops_0.5", 32), ("resnet50", "bops_0.5", 16)])
+                                                  ("resnet18", "bops_0.5", 32), ("resnet50", "bops_0.5", 16),
+                                                  ("resnet101", "uniform4", 16)])
 def test_frozen_graph_matches_golden(monkeypatch, arch, scheme, res_bits):
     abi_model.install_cpu_backend(monkeypatch)
     logits_g, meta = load_net_golden(arch, scheme)

@@ -13,7 +13,7 @@ from tests.util import build_fakequant, golden_act_ranges, load_net_golden, sha_
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 CONFIGS = [("resnet18", "uniform8"), ("resnet18", "uniform4"), ("resnet18", "bops_0.5"),
-           ("resnet50", "uniform8"), ("resnet50", "uniform4"), ("resnet50", "bops_0.5")]
+           ("resnet50", "uniform8"), ("resnet50", "uniform4"), ("resnet50", "bops_0.5"), ("resnet101", "uniform8")]
 
 
 def _model(arch, scheme, meta):

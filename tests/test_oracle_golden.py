@@ -113,7 +113,7 @@ def test_module_kats():
 
 
 @pytest.mark.parametrize("arch,scheme", [("resnet18", "uniform8"), ("resnet18", "uniform4"), ("resnet18", "bops_0.5"),
-                                         ("resnet50", "bops_0.5")])
+                                         ("resnet50", "bops_0.5"), ("resnet101", "uniform8")])
 def test_network_golden(arch, scheme):
     """Whole network: fakequant and int_ref reproduce the reference's activation integers (sha256 over every
     QuantAct output), integer weights and bit-equal logits."""
