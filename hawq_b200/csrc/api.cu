@@ -102,6 +102,20 @@ static int set_tc_attr1() {
   CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64, EPI, WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, EPI, true>::TOTAL));
   return HAWQ_OK;
 }
+// 16-epilogue-warp variants (uint16-stream epilogues, 128-column tiles)
+template <int EPI>
+static int set_tc_attr_ew16() {
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, false, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI, false, 16>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, true, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI, false, 16>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, false, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI, true, 16>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, true, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI, true, 16>::TOTAL));
+  return HAWQ_OK;
+}
+static bool epi16_enabled() {
+  static const bool on = [] { const char* e = getenv("HAWQ_B200_EPI16"); return e && e[0] == '1'; }();   // opt-in until validated on hardware
+  return on;
+}
+
 template <int EPI>
 static int set_tc_attr() {
   int rc = set_tc_attr1<EPI, false>();
@@ -111,24 +125,27 @@ static int set_tc_attr() {
 
 // conv_tc launches carry the programmatic-stream-serialization attribute (HAWQ_B200_PDL != 0): the kernel's prologue may
 // start while the previous kernel of the stream drains; the kernel itself waits (griddepcontrol.wait) before touching memory
-template <int BN, int EPI, bool WIDE, bool A4>
+template <int BN, int EPI, bool WIDE, bool A4, int EW = TC_EPI_WARPS>
 static void launch_tc3(const ConvParams& p, const TcMaps& maps, int grid, cudaStream_t st) {
   static const bool pdl = [] { const char* e = getenv("HAWQ_B200_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(TC_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = TcSmem<BN, EPI, A4>::TOTAL;
+  cfg.blockDim = dim3(tc_threads(EW), 1, 1);
+  cfg.dynamicSmemBytes = TcSmem<BN, EPI, A4, EW>::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, EPI, WIDE, A4>, p, maps);   // errors surface through launch_check()
+  cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, EPI, WIDE, A4, EW>, p, maps);   // errors surface through launch_check()
 }
 template <int EPI, bool WIDE, bool A4>
 static void launch_tc2(const ConvParams& p, const TcMaps& maps, bool bn128, int grid, cudaStream_t st) {
+  if constexpr (EPI == TC_EPI_RES22 || EPI == TC_EPI_DUAL) {
+    if (bn128 && p.epi16) { launch_tc3<128, EPI, WIDE, A4, 16>(p, maps, grid, st); return; }
+  }
   if (bn128) launch_tc3<128, EPI, WIDE, A4>(p, maps, grid, st);
   else launch_tc3<64, EPI, WIDE, A4>(p, maps, grid, st);
 }
@@ -172,7 +189,8 @@ int hawq_create(int device, hawq_handle** out) {
   CUDA_TRY(cudaMemset(h->status, 0, sizeof(int32_t)));
   int rc;
   if ((rc = set_tc_attr<TC_EPI_REQ>()) || (rc = set_tc_attr<TC_EPI_RAW>()) || (rc = set_tc_attr<TC_EPI_RES22>()) ||
-      (rc = set_tc_attr<TC_EPI_RES44>()) || (rc = set_tc_attr<TC_EPI_RES42>()) || (rc = set_tc_attr<TC_EPI_DUAL>()))
+      (rc = set_tc_attr<TC_EPI_RES44>()) || (rc = set_tc_attr<TC_EPI_RES42>()) || (rc = set_tc_attr<TC_EPI_DUAL>()) ||
+      (rc = set_tc_attr_ew16<TC_EPI_RES22>()) || (rc = set_tc_attr_ew16<TC_EPI_DUAL>()))
     return rc;
   CUDA_TRY(cudaFuncSetAttribute(linear_dp4a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, linear_smem_bytes(LIN_MAX_K)));
   if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
@@ -332,7 +350,8 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
       p.patch_rows = (int)rows;
     }
     if (ep->mode == HAWQ_EPI_RESIDUAL && ep->res_kind == 0 && ep->res_bits == 16 && ep->y_bits == 16) {
-      const uint32_t cw = bn / 2;   // columns per epilogue warp
+      p.epi16 = (epi16_enabled() && bn == 128) ? 1 : 0;
+      const uint32_t cw = p.epi16 ? bn / 4 : bn / 2;   // columns per epilogue warp
       const CUtensorMapSwizzle sw_y = cw * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
       int bad = make_map_2d(&maps.res, res, (uint64_t)d->Cout * 2, (uint64_t)M, (uint64_t)d->Cout * 2, cw * 2, 32, sw_y);
       bad |= make_map_2d(&maps.y, out, (uint64_t)d->Cout * 2, (uint64_t)M, (uint64_t)d->Cout * 2, cw * 2, 32, sw_y);
@@ -418,7 +437,8 @@ int hawq_conv2d_dual(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogu
 
   const bool a4 = d->a_bits == 4;
   const bool bn128 = (d->Cout % 128 == 0);
-  const uint32_t cw = (bn128 ? 128 : 64) / 2;
+  p.epi16 = (epi16_enabled() && bn128) ? 1 : 0;
+  const uint32_t cw = p.epi16 ? 32 : (bn128 ? 128 : 64) / 2;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   const CUtensorMapSwizzle sw_y = cw * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;

@@ -44,15 +44,16 @@ struct ConvParams {
   int tma_io;        // tcgen05 kernel: uint16 residual tile in / outputs out through TMA
   const int8_t* w_tiled;  // tcgen05 kernel: weights re-tiled into contiguous pre-swizzled [n_tile][k_tile][BN][64] blocks
   int patch_rows;    // tcgen05 kernel, 3x3 stride-1 pad-1 layers: rows of the shared-memory input patch (128 + 2W + 2), 0 = gather mode
+  int sat_pack;           // tcgen05 RESIDUAL epilogues: 8-bit low copy packed with cvt.pack.sat when its clamp is [<= 0, 127]
   // tcgen05 dual mode (resize units): the identity-branch 1x1 convolution is computed in the same kernel into a second
   // TMEM accumulator instead of round-tripping an int32 tensor through HBM
-  int sat_pack;           // tcgen05 RESIDUAL epilogues: 8-bit low copy packed with cvt.pack.sat when its clamp is [<= 0, 127]
   int dual;               // 0 / 1
   const uint8_t* x2;      // identity conv input (same a_bits as x)
   const int8_t* w2_tiled; // its re-tiled weights
   const hawq_chan* chan2; // its bias and the case-1 identity ratio (m1, e1) per channel
   int H2, W2, stride2, cin_chunks2, x2_pix_bytes;
   long long* trace;  // debug timeline (hawq_debug_set_trace): [role][tile][event] clock64 values of CTA 0, or null
+  int epi16;              // host-side launch choice: 16-epilogue-warp variant of the uint16-stream kernels (maps built for BN / 4 columns)
 };
 
 constexpr int CONV_BM = 128;

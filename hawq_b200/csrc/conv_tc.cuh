@@ -42,9 +42,12 @@ struct alignas(64) TcMaps {
 
 constexpr int TC_BM = 128;
 constexpr int TC_PRODUCER_WARPS = 4;
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 8;          // default epilogue width; the EW = 16 variants (RES22 / DUAL, BN = 128) use 16 warps
 constexpr int TC_MMA_WARP = TC_PRODUCER_WARPS;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + TC_EPI_WARPS) * 32;   // 416
+// EW = 16: warps 0-3 producers, 4 MMA, 5-7 idle (register donors: setmaxnreg works on aligned groups of 4 warps), 8-23 epilogue
+__host__ __device__ constexpr int tc_epi_warp0(int ew) { return ew == 16 ? 8 : TC_MMA_WARP + 1; }
+__host__ __device__ constexpr int tc_threads(int ew) { return ew == 16 ? 24 * 32 : TC_THREADS; }
 
 // epilogue variants (compile-time): element sizes of the residual operand read into / the output staged in the slice
 constexpr int TC_EPI_REQ = 0;      // REQUANT -> 4/8 bit
@@ -54,8 +57,9 @@ constexpr int TC_EPI_RES44 = 3;    // RESIDUAL: int32 in (stream or identity-con
 constexpr int TC_EPI_RES42 = 4;    // RESIDUAL: int32 in, uint16 out
 constexpr int TC_EPI_DUAL = 5;     // RESIDUAL whose identity operand is a second in-kernel 1x1 convolution (two TMEM accumulators), uint16 out
 
-template <int BN, int EPI, bool A4 = false>
+template <int BN, int EPI, bool A4 = false, int EW = TC_EPI_WARPS>
 struct TcSmem {
+  static_assert(EW == 8 || (EW == 16 && BN == 128), "16 epilogue warps: 128-column tiles only");
   // pipeline depth: RESIDUAL epilogues are epilogue-bound and need shared memory for their tiles; the others are
   // load-latency-bound and get a deep ring.  The producer keeps LAG + 1 k-tiles in flight per thread.
   static constexpr int STAGES = (EPI == TC_EPI_RES22) ? (A4 && BN == 128 ? 4 : 5) : (EPI == TC_EPI_DUAL) ? 6 : (EPI >= TC_EPI_RES44) ? 5 : (EPI == TC_EPI_RAW) ? 7 : (BN == 128 ? 8 : 10);
@@ -64,19 +68,19 @@ struct TcSmem {
   static constexpr int B_STAGE = BN * 64;
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int RING = STAGES * STAGE;
-  static constexpr int CW = BN / 2;                                        // columns per epilogue warp
+  static constexpr int CW = BN / (EW / 4);                                 // columns per epilogue warp (4 warps cover the 128 TMEM lanes)
   static constexpr int RES_ES = (EPI == TC_EPI_RES22) ? 2 : ((EPI == TC_EPI_RES44 || EPI == TC_EPI_RES42) ? 4 : 0);
   static constexpr int Y_ES = (EPI == TC_EPI_RES22 || EPI == TC_EPI_RES42 || EPI == TC_EPI_DUAL) ? 2 : ((EPI == TC_EPI_RES44 || EPI == TC_EPI_RAW) ? 4 : 0);
   static constexpr int SLICE_ES = RES_ES > Y_ES ? RES_ES : Y_ES;
   static constexpr bool TMA_IO = (EPI == TC_EPI_RES22 || EPI == TC_EPI_DUAL);                    // residual tile in / outputs out as swizzled TMA boxes
   static constexpr int SLICE_PITCH = TMA_IO ? CW * SLICE_ES : CW * SLICE_ES + 16;   // padded: 16-byte row-per-lane accesses conflict-free
-  static constexpr int SLICE = SLICE_ES ? (TMA_IO ? 4096 : 32 * SLICE_PITCH) : 0;
+  static constexpr int SLICE = SLICE_ES ? (TMA_IO ? (EW == 8 ? 4096 : 32 * CW * 2) : 32 * SLICE_PITCH) : 0;
   static constexpr int SLICE_BUFS = (EPI == TC_EPI_RES22) ? 3 : 1;         // RES22: 2 prefetch + 1 output; RES4x: in place; RAW: output
   static constexpr int LOW_PITCH = TMA_IO ? CW : CW + 16;
-  static constexpr int LOW_SLICE = (EPI == TC_EPI_RAW) ? 0 : (TMA_IO ? 2048 : 32 * LOW_PITCH);   // TMA boxes keep 1024 B alignment
+  static constexpr int LOW_SLICE = (EPI == TC_EPI_RAW) ? 0 : (TMA_IO ? (EW == 8 ? 2048 : 32 * CW) : 32 * LOW_PITCH);   // TMA boxes keep 1024 B alignment
   static constexpr int SLICES_OFF = RING;
-  static constexpr int LOW_OFF = SLICES_OFF + TC_EPI_WARPS * SLICE * SLICE_BUFS;
-  static constexpr int CST_OFF = LOW_OFF + TC_EPI_WARPS * LOW_SLICE;       // double2 {Cb, M}[BN]
+  static constexpr int LOW_OFF = SLICES_OFF + EW * SLICE * SLICE_BUFS;
+  static constexpr int CST_OFF = LOW_OFF + EW * LOW_SLICE;       // double2 {Cb, M}[BN]
   static constexpr int M1_OFF = CST_OFF + BN * 16;                         // double M1[BN]  (DUAL: double2 {Cb2, M1}[BN])
   static constexpr int STG_SLOT = TC_BM * 32;                              // packed 4-bit rows of one k-tile (A4 only)
   static constexpr int STG_OFF = M1_OFF + BN * (EPI == TC_EPI_DUAL ? 16 : 8);
@@ -214,9 +218,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n, bool a_signed
 // K order the (host-permuted) weights expect: per 32-channel block {c0-3, c8-11, c16-19, c24-27 | c4-7, c12-15, ...}.
 // Preconditions (promised via HAWQ_EP_RATIOS_*, re-checked -> HAWQ_FLAG_BAD_RATIO): ratios within the bound,
 // |bias| < 2^29 (sums of two requantised terms then cannot wrap), RESIDUAL launches have relu = 1.
-template <int BN, int EPI, bool WIDE, bool A4>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams p, const __grid_constant__ TcMaps maps) {
-  using S = TcSmem<BN, EPI, A4>;
+// EW: epilogue warps.  8 (default) or 16: the uint16-stream epilogues are instruction-latency bound with two epilogue warps
+// per SM sub-partition (profiles/r01/d1_ncu_full_conv_tc.txt: 45 % issue utilisation, "wait" stalls dominate); with 16 warps
+// each TMEM lane quarter is served by four warps of BN / 4 columns and registers are moved from the producer / MMA warp
+// groups to the epilogue groups with setmaxnreg.  Opt-in (HAWQ_B200_EPI16=1) until validated on hardware.
+template <int BN, int EPI, bool WIDE, bool A4, int EW = TC_EPI_WARPS>
+__global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvParams p, const __grid_constant__ TcMaps maps) {
+  using S = TcSmem<BN, EPI, A4, EW>;
+  constexpr int EPI_WARP0 = tc_epi_warp0(EW);    // first epilogue warp
   constexpr int BM = TC_BM, STAGES = S::STAGES, LAG = S::LAG;
   constexpr int CW = S::CW;                      // columns handled by one epilogue warp: 32 or 64
   constexpr int TMEM_COLS = (EPI == TC_EPI_DUAL ? 4 : 2) * BN;   // two accumulator buffers (x2 accumulators in dual mode): 128 / 256 / 512
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::BAR_OFF + 8 * (2 * STAGES + 4));
   auto res_bar = [&](int ew_, int b) { return bar_base + 8u * (2 * STAGES + 6 + ew_ * 2 + b); };   // TMA residual tiles (per epilogue warp)
-  auto patch_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 22 + b); };                    // TMA input patches (3x3 patch mode)
+  auto patch_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + 2 * EW + b); };            // TMA input patches (3x3 patch mode)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // debug timeline: role 0 producer (warp 0), 1 MMA, 2 epilogue (first epilogue warp); 8 events x 64 tiles per role
@@ -258,8 +267,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), TC_EPI_WARPS);
-      for (int w = 0; w < TC_EPI_WARPS; ++w) mbar_init(res_bar(w, b), 1);
+      mbar_init(tempty_bar(b), EW);
+      for (int w = 0; w < EW; ++w) mbar_init(res_bar(w, b), 1);
       mbar_init(patch_bar(b), 1);
     }
     fence_barrier_init();
@@ -275,8 +284,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
   // global memory is read and written: wait until the preceding grid has completed and flushed.  Both are no-ops otherwise.
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // EW == 16: 768 threads x 80 registers at launch; the producer and MMA warp groups give registers to the four epilogue groups
+  // (setmaxnreg sits at the top of each role branch so that ptxas allocates every role against its own budget)
 
   if (warp < TC_PRODUCER_WARPS) {
+    if constexpr (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     // =============================================================================== producers (128 threads)
     // Coalesced gather: consecutive lanes cover one row's bytes (4 lanes x 16 B = 64 B int8 row, 2 lanes x 16 B = packed
     // 4-bit row), so a warp-level cp.async touches 8 (16) cache lines instead of 32.  Each thread serves A_PASSES rows.
@@ -481,9 +493,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
     fence_proxy_async();
     for (uint32_t j = pending; j > 0; --j) mbar_arrive(full_bar((it - j) % STAGES));
     }
-  } else if (warp == TC_MMA_WARP) {
+  } else if (warp == TC_MMA_WARP || (EW == 16 && warp < EPI_WARP0)) {
+    if constexpr (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // warps 4-7 (5-7 only donate registers)
     // =============================================================================== MMA issuer (one lane)
-    if (lane == 0) {
+    if (warp == TC_MMA_WARP && lane == 0) {
       const uint32_t idesc = umma_idesc_i8(BM, BN, !A4);   // packed 4-bit activations are unsigned
       uint32_t it = 0, tile_iter = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
@@ -511,10 +524,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
       }
     }
   } else {
-    // =============================================================================== epilogue (8 warps)
-    const int ew = warp - (TC_MMA_WARP + 1);     // 0..7
+    if constexpr (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    // =============================================================================== epilogue (EW warps)
+    const int ew = warp - EPI_WARP0;             // 0..EW-1
     const int quarter = warp & 3;                // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                    // column half
+    const int half = ew >> 2;                    // column block of CW columns (2 halves, or 4 quarters when EW = 16)
     // slices: RES22 -> [0],[1] residual prefetch ring, [2] output; RES4x -> [0] residual in / output in place; RAW -> [0] output
     uint8_t* slice0 = smem + S::SLICES_OFF + ew * S::SLICE * S::SLICE_BUFS;
     uint8_t* yslice = slice0 + (S::SLICE_BUFS - 1) * S::SLICE;
@@ -592,8 +606,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
 
       // per-channel constants of this tile's channel block (shared by the 8 epilogue warps)
       if (n0 != cur_n0) {
-        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32));     // everyone finished reading the previous block
-        for (int i = tid - (TC_MMA_WARP + 1) * 32; i < BN; i += TC_EPI_WARPS * 32) {
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32));     // everyone finished reading the previous block
+        for (int i = tid - EPI_WARP0 * 32; i < BN; i += EW * 32) {
           const hawq_chan ch = p.chan[n0 + i];
           sCst[i] = make_double2(kOffS - (double)ch.bias, dyadic_to_double(ch.m, ch.e));
           bad |= !ratio_ok(ch.m, ch.e) | (ch.bias >= (1 << 29)) | (ch.bias <= -(1 << 29));
@@ -611,7 +625,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams
             }
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32));
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32));
         cur_n0 = n0;
       }
 
