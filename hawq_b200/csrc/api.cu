@@ -111,6 +111,17 @@ static int set_tc_attr_ew16() {
   CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, true, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI, true, 16>::TOTAL));
   return HAWQ_OK;
 }
+static int set_tc_attr_lean() {
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, TC_EPI_REQ, false, false, TC_EPI_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, TC_EPI_REQ, false>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64, TC_EPI_REQ, false, false, TC_EPI_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, TC_EPI_REQ, false>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, TC_EPI_REQ, false, true, TC_EPI_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, TC_EPI_REQ, true>::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64, TC_EPI_REQ, false, true, TC_EPI_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, TC_EPI_REQ, true>::TOTAL));
+  return HAWQ_OK;
+}
+static bool mma_fast_enabled() {
+  static const bool on = [] { const char* e = getenv("HAWQ_B200_MMA_FAST"); return e && e[0] == '1'; }();   // opt-in until validated on hardware
+  return on;
+}
 static bool epi16_enabled() {
   static const bool on = [] { const char* e = getenv("HAWQ_B200_EPI16"); return e && e[0] == '1'; }();   // opt-in until validated on hardware
   return on;
@@ -125,7 +136,7 @@ static int set_tc_attr() {
 
 // conv_tc launches carry the programmatic-stream-serialization attribute (HAWQ_B200_PDL != 0): the kernel's prologue may
 // start while the previous kernel of the stream drains; the kernel itself waits (griddepcontrol.wait) before touching memory
-template <int BN, int EPI, bool WIDE, bool A4, int EW = TC_EPI_WARPS>
+template <int BN, int EPI, bool WIDE, bool A4, int EW = TC_EPI_WARPS, bool LEAN = false>
 static void launch_tc3(const ConvParams& p, const TcMaps& maps, int grid, cudaStream_t st) {
   static const bool pdl = [] { const char* e = getenv("HAWQ_B200_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg;
@@ -139,12 +150,19 @@ static void launch_tc3(const ConvParams& p, const TcMaps& maps, int grid, cudaSt
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, EPI, WIDE, A4, EW>, p, maps);   // errors surface through launch_check()
+  cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, EPI, WIDE, A4, EW, LEAN>, p, maps);   // errors surface through launch_check()
 }
 template <int EPI, bool WIDE, bool A4>
 static void launch_tc2(const ConvParams& p, const TcMaps& maps, bool bn128, int grid, cudaStream_t st) {
   if constexpr (EPI == TC_EPI_RES22 || EPI == TC_EPI_DUAL) {
     if (bn128 && p.epi16) { launch_tc3<128, EPI, WIDE, A4, 16>(p, maps, grid, st); return; }
+  }
+  if constexpr (EPI == TC_EPI_REQ && !WIDE) {
+    if (p.mma_fast) {
+      if (bn128) launch_tc3<128, EPI, WIDE, A4, TC_EPI_WARPS, true>(p, maps, grid, st);
+      else launch_tc3<64, EPI, WIDE, A4, TC_EPI_WARPS, true>(p, maps, grid, st);
+      return;
+    }
   }
   if (bn128) launch_tc3<128, EPI, WIDE, A4>(p, maps, grid, st);
   else launch_tc3<64, EPI, WIDE, A4>(p, maps, grid, st);
@@ -190,7 +208,7 @@ int hawq_create(int device, hawq_handle** out) {
   int rc;
   if ((rc = set_tc_attr<TC_EPI_REQ>()) || (rc = set_tc_attr<TC_EPI_RAW>()) || (rc = set_tc_attr<TC_EPI_RES22>()) ||
       (rc = set_tc_attr<TC_EPI_RES44>()) || (rc = set_tc_attr<TC_EPI_RES42>()) || (rc = set_tc_attr<TC_EPI_DUAL>()) ||
-      (rc = set_tc_attr_ew16<TC_EPI_RES22>()) || (rc = set_tc_attr_ew16<TC_EPI_DUAL>()))
+      (rc = set_tc_attr_ew16<TC_EPI_RES22>()) || (rc = set_tc_attr_ew16<TC_EPI_DUAL>()) || (rc = set_tc_attr_lean()))
     return rc;
   CUDA_TRY(cudaFuncSetAttribute(linear_dp4a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, linear_smem_bytes(LIN_MAX_K)));
   if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
@@ -275,6 +293,7 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   p.patch_rows = 0;
   p.w_tiled = nullptr;
   p.sat_pack = sat_pack_enabled() ? 1 : 0;
+  p.mma_fast = mma_fast_enabled() ? 1 : 0;
   if (ep->mode == HAWQ_EPI_RESIDUAL) {
     if (ep->res_kind == 0 && !dyadic_is_fast(ep->res_m, ep->res_e)) p.slow_scalar = 1;
     if (ep->low_bits != 0 && !dyadic_is_fast(ep->low_m, ep->low_e)) p.slow_scalar = 1;
@@ -431,6 +450,7 @@ int hawq_conv2d_dual(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogu
   p.w_tiled = w + (size_t)d->Cout * d->Cin;
   p.dual = 1;
   p.sat_pack = sat_pack_enabled() ? 1 : 0;
+  p.mma_fast = mma_fast_enabled() ? 1 : 0;
   p.x2 = (const uint8_t*)x2; p.w2_tiled = w2 + (size_t)d2->Cout * d2->Cin; p.chan2 = chan2;
   p.H2 = d2->H; p.W2 = d2->W; p.stride2 = d2->stride; p.cin_chunks2 = d2->Cin / 64; p.x2_pix_bytes = d2->Cin * d2->a_bits / 8;
   p.tma_io = 1;

@@ -222,7 +222,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n, bool a_signed
 // per SM sub-partition (profiles/r01/d1_ncu_full_conv_tc.txt: 45 % issue utilisation, "wait" stalls dominate); with 16 warps
 // each TMEM lane quarter is served by four warps of BN / 4 columns and registers are moved from the producer / MMA warp
 // groups to the epilogue groups with setmaxnreg.  Opt-in (HAWQ_B200_EPI16=1) until validated on hardware.
-template <int BN, int EPI, bool WIDE, bool A4, int EW = TC_EPI_WARPS>
+// LEAN: lean MMA issue loop (REQUANT kernels, opt-in HAWQ_B200_MMA_FAST=1), see the comment at the loop.
+template <int BN, int EPI, bool WIDE, bool A4, int EW = TC_EPI_WARPS, bool LEAN = false>
 __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvParams p, const __grid_constant__ TcMaps maps) {
   using S = TcSmem<BN, EPI, A4, EW>;
   constexpr int EPI_WARP0 = tc_epi_warp0(EW);    // first epilogue warp
@@ -499,6 +500,38 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
     if (warp == TC_MMA_WARP && lane == 0) {
       const uint32_t idesc = umma_idesc_i8(BM, BN, !A4);   // packed 4-bit activations are unsigned
       uint32_t it = 0, tile_iter = 0;
+      if constexpr (LEAN) {
+        // Lean issue loop (opt-in, HAWQ_B200_MMA_FAST=1).  ncu source counters (profiles/r01/experiments/README.md) show the
+        // issuing lane is the pacing resource of the REQUANT layers: ~60 dependent instructions per k-tile.  Here the ring
+        // position is tracked incrementally, the shared-memory descriptors advance by constants (low word = address >> 4 |
+        // 1 << 16, the high word never changes), the generic->async proxy fence is issued only when the A tile was written by
+        // plain cp.async (the other producers fence before they arrive, TMA needs none), and there is no tracing.
+        const bool consumer_fence = !A4 && p.tma_a == 0 && !(EPI == TC_EPI_REQ && p.patch_rows != 0);
+        const uint64_t desc_hi = umma_desc_sw64(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t a_lo0 = (smem_base >> 4) | (1u << 16);
+        uint32_t stage = 0, phase = 0, a_lo = a_lo0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+          const int buf = tile_iter & 1;
+          mbar_wait(tempty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem0 = tmem_base + buf * ACC_STRIDE;
+          for (int kt = 0; kt < KT; ++kt) {
+            const uint32_t d_tmem = d_tmem0 + ((DUAL && kt >= KT1) ? BN : 0);
+            mbar_wait(full_bar(stage), phase);
+            if (consumer_fence) fence_proxy_async();
+            tc_fence_after();
+            const uint32_t b_lo = a_lo + (S::A_STAGE >> 4);
+            const uint32_t first = (kt != 0 && !(DUAL && kt == KT1)) ? 1u : 0u;
+            umma_i8(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, first);
+            umma_i8(d_tmem, desc_hi | (a_lo + 2), desc_hi | (b_lo + 2), idesc, 1u);
+            umma_commit(empty_bar(stage));
+            if (kt == KT - 1) umma_commit(tfull_bar(buf));
+            ++stage;
+            a_lo += (S::STAGE >> 4);
+            if (stage == STAGES) { stage = 0; phase ^= 1; a_lo = a_lo0; }
+          }
+        }
+      } else {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
         const int buf = tile_iter & 1;
         trace(1, tile_iter, 0);
@@ -521,6 +554,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
           umma_commit(empty_bar(stage));                          // smem stage reusable once these MMAs retire
           if (kt == KT - 1) { umma_commit(tfull_bar(buf)); trace(1, tile_iter, 3); }   // accumulator complete
         }
+      }
       }
     }
   } else {
