@@ -141,6 +141,16 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one lane of a converged warp
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
@@ -497,7 +507,12 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
   } else if (warp == TC_MMA_WARP || (EW == 16 && warp < EPI_WARP0)) {
     if constexpr (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // warps 4-7 (5-7 only donate registers)
     // =============================================================================== MMA issuer (one lane)
-    if (warp == TC_MMA_WARP && lane == 0) {
+    // LEAN: the issuing lane is chosen with elect.sync by the converged warp; nvcc then emits straight-line UTCIMMA / UTCBAR,
+    // whereas issue from a `lane == 0` branch is wrapped in an ELECT + BRA.U.ANY loop per instruction.
+    uint32_t issuer;
+    if constexpr (LEAN) issuer = elect_one();
+    else issuer = (warp == TC_MMA_WARP && lane == 0) ? 1u : 0u;
+    if (issuer) {
       const uint32_t idesc = umma_idesc_i8(BM, BN, !A4);   // packed 4-bit activations are unsigned
       uint32_t it = 0, tile_iter = 0;
       if constexpr (LEAN) {
