@@ -78,3 +78,66 @@ def test_host_requant_exact_ties(lib, q, k, odd_shift):
         return                                           # not a tie for this (m, e): covered by the generic property
     got = lib.hawq_rhe_requant_host(v, m, e)
     assert got == rhe_exact(v, m, e) and got % 2 == 0
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# The arithmetic of the fused epilogues (hawq_b200/csrc/common.cuh, conv_tc.cuh), modelled with exact rationals: one FP64 FMA with
+# the 1.5 * 2^52 constant rounds (v + bias) * m / 2^e once, to nearest-even, and the low mantissa word is the integer result.
+# float(Fraction) is correctly rounded, so this checks the ALGORITHM (not the CUDA code, which the -m gpu tests cover).
+import struct  # noqa: E402
+
+MAGIC = 3 * 2 ** 51            # 1.5 * 2^52
+OFF_S = 2 ** 52 + 2 ** 31      # double({0x43300000, v ^ 0x80000000}) = 2^52 + 2^31 + v
+OFF_U = 2 ** 52                # double({0x43300000, u})              = 2^52 + u
+
+
+def _lo_word(y):
+    bits = struct.unpack("<Q", struct.pack("<d", y))[0]
+    lo = bits & 0xFFFFFFFF
+    return lo - 2 ** 32 if lo >= 2 ** 31 else lo, bits >> 32
+
+
+def fast_signed(v, bias, m, e):
+    d = float(OFF_S + v)                                   # exact: < 2^53
+    cb = float(OFF_S - bias)                               # exact
+    dv = d - cb                                            # exact: v + bias
+    assert Fraction(dv) == v + bias
+    y = float(Fraction(dv) * Fraction(m, 2 ** e) + MAGIC)  # the FMA: one rounding
+    return _lo_word(y)
+
+
+def fast_unsigned_folded(u, m, e):
+    big_m = Fraction(m, 2 ** e)
+    c = float(Fraction(MAGIC) - OFF_U * big_m)
+    assert Fraction(c) == Fraction(MAGIC) - OFF_U * big_m  # the folded constant is exact for e <= 51
+    y = float(Fraction(OFF_U + u) * big_m + Fraction(c))
+    return _lo_word(y)[0]
+
+
+@settings(max_examples=600, deadline=None)
+@given(st.integers(-2 ** 30, 2 ** 30), st.integers(-2 ** 29 + 1, 2 ** 29 - 1), st.integers(0, 2 ** 31), st.integers(31, 62))
+def test_fma_requant_is_exact_for_ratios_up_to_one(v, bias, m, e):
+    q, _ = fast_signed(v, bias, m, e)
+    assert q == rhe_exact(v + bias, m, e)
+
+
+@settings(max_examples=600, deadline=None)
+@given(st.integers(-2 ** 30, 2 ** 30), st.integers(-2 ** 20, 2 ** 20), st.integers(2 ** 30, 2 ** 31), st.integers(11, 40))
+def test_fma_requant_wide_ratios_with_overflow_check(v, bias, m, e):
+    """ratios up to 2^20: the result is exact whenever the kernel's validity check passes, and the check fails exactly when the
+    rounded value leaves int32 (then HAWQ_FLAG_REQUANT_OVERFLOW is raised and the saturating kernels are used)."""
+    q, hi = fast_signed(v, bias, m, e)
+    exact = Fraction((v + bias) * m, 2 ** e)
+    fl = math.floor(exact)
+    rem = exact - fl
+    r = fl + (1 if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and fl % 2 == 1) else 0)   # unsaturated RHE
+    valid = ((hi + ((q >> 31) & 1)) ^ 0x43380000) == 0                                       # the check in conv_tc.cuh (WIDE)
+    assert valid == (-2 ** 31 <= r < 2 ** 31)
+    if valid:
+        assert q == r
+
+
+@settings(max_examples=600, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(0, 2 ** 31), st.integers(31, 51))
+def test_folded_unsigned_fma_is_exact(u, m, e):
+    assert fast_unsigned_folded(u, m, e) == rhe_exact(u, m, e)
