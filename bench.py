@@ -197,7 +197,8 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU (the product has no CPU path); use --impl reference for the CPU arm")
-    torch.set_num_threads(usable_cpus())            # CPU-side calibration / plan building
+    # CPU-side calibration / plan building: share the usable host cores between the ranks of this node
+    torch.set_num_threads(max(1, usable_cpus() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
