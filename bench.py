@@ -19,7 +19,6 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "images/sec ResNet-50 W8A8 & W4A4 @batch128, 1/2/4/8xB200; % int-TC roofline"

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (EPI_DEQUANT_F32, EPI_RAW_I32, EPI_REQUANT, EPI_RESIDUAL, hawq_conv_desc, hawq_epilogue_desc)
+from ._lib import EPI_RAW_I32, EPI_REQUANT, EPI_RESIDUAL, hawq_conv_desc, hawq_epilogue_desc
 
 _handles = {}
 launch_count = 0   # number of kernels launched through this module (bench reports it as gpu_launches)

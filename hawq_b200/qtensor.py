@@ -19,7 +19,7 @@ import os
 import torch
 
 from . import ops, quant_math as qmath
-from ._lib import EPI_DEQUANT_F32, EPI_RAW_I32, EPI_REQUANT, EPI_RESIDUAL, EP_RATIOS_LE_ONE, ERR_UNSUPPORTED, HawqError
+from ._lib import EPI_RAW_I32, EPI_REQUANT, EPI_RESIDUAL, ERR_UNSUPPORTED, HawqError
 
 
 class EngineConfig:
