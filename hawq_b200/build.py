@@ -36,15 +36,29 @@ def up_to_date():
 
 
 def build_library(force=False, verbose=False, extra_flags=()):
-    """Compile every .cu under csrc/ into hawq_b200/libhawq_b200.so.  Returns the path."""
+    """Compile every .cu under csrc/ into hawq_b200/libhawq_b200.so.  Returns the path.
+    Safe when several processes call it at once (one rank per GPU under torchrun): an exclusive file lock serialises them, the
+    winner compiles into a temporary file and renames it into place, the others find the library up to date."""
     if not force and up_to_date():
         return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-I", INCLUDE, "-o", OUT] + sources()
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout)
-    if verbose and r.stdout:
-        print(r.stdout)
+    import fcntl
+    with open(OUT + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and up_to_date():               # another process built it while we waited
+                return OUT
+            tmp = "%s.tmp.%d" % (OUT, os.getpid())
+            cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-I", INCLUDE, "-o", tmp] + sources()
+            if verbose:
+                print(" ".join(cmd).replace(tmp, OUT))
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + r.stdout)
+            os.replace(tmp, OUT)
+            if verbose and r.stdout:
+                print(r.stdout)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return OUT
