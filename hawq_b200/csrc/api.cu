@@ -208,7 +208,9 @@ int hawq_create(int device, hawq_handle** out) {
   int rc;
   if ((rc = set_tc_attr<TC_EPI_REQ>()) || (rc = set_tc_attr<TC_EPI_RAW>()) || (rc = set_tc_attr<TC_EPI_RES22>()) ||
       (rc = set_tc_attr<TC_EPI_RES44>()) || (rc = set_tc_attr<TC_EPI_RES42>()) || (rc = set_tc_attr<TC_EPI_DUAL>()) ||
-      (rc = set_tc_attr_ew16<TC_EPI_RES22>()) || (rc = set_tc_attr_ew16<TC_EPI_DUAL>()) || (rc = set_tc_attr_lean()))
+      // opt-in variants: configured only when requested, so the default start-up sequence is exactly the validated one
+      (epi16_enabled() && ((rc = set_tc_attr_ew16<TC_EPI_RES22>()) || (rc = set_tc_attr_ew16<TC_EPI_DUAL>()))) ||
+      (mma_fast_enabled() && (rc = set_tc_attr_lean())))
     return rc;
   CUDA_TRY(cudaFuncSetAttribute(linear_dp4a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, linear_smem_bytes(LIN_MAX_K)));
   if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
