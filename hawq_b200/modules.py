@@ -120,11 +120,14 @@ class QuantAct(Module):
 
     def forward(self, x, pre_act_scaling_factor=None, pre_weight_scaling_factor=None, identity=None,
                 identity_scaling_factor=None, identity_weight_scaling_factor=None):
+        channel_num = x[2] if type(x) is tuple and len(x) == 3 else None     # multi-branch input (quant_modules.py:219-223)
         x, pre_act_scaling_factor = _split(x, pre_act_scaling_factor)
         _check_mode(self.quant_mode)
         if self.full_precision_flag:
             return x
         if not self.running_stat:
+            if type(pre_act_scaling_factor) is list:
+                raise NotImplementedError("frozen multi-branch QuantAct (Inception concat) has no integer kernel yet")
             return _frozen_dispatch(self, "act_forward", x, pre_act_scaling_factor, pre_weight_scaling_factor,
                                     identity, identity_scaling_factor, identity_weight_scaling_factor)
         # ---- un-frozen: observe + float emulation (calibration) ----
@@ -134,7 +137,15 @@ class QuantAct(Module):
         if pre_act_scaling_factor is None or self.fixed_point_quantization:
             q = qmath.quantize(x, self.activation_bit, sf, signed=(self.quant_mode == "symmetric"))
         elif type(pre_act_scaling_factor) is list:
-            raise NotImplementedError("multi-branch QuantAct (Inception concat) is outside the ResNet hot path")
+            # concatenated branches, each with its own input scale (quant_modules.py:275-286): case 0 per channel slice with
+            # weight scale s_i / s_i = 1
+            if channel_num is None or len(channel_num) != len(pre_act_scaling_factor):
+                raise ValueError("multi-branch QuantAct needs (x, [scales], [channels per branch])")
+            q = x.clone()
+            start = 0
+            for s_i, n_i in zip(pre_act_scaling_factor, channel_num):
+                q[:, start:start + n_i] = qmath.float_case0(x[:, start:start + n_i], self.activation_bit, self.quant_mode, sf, s_i, s_i / s_i)
+                start += n_i
         elif identity is None:
             if pre_weight_scaling_factor is None:
                 pre_weight_scaling_factor = self.pre_weight_scaling_factor

@@ -229,9 +229,31 @@ def make_net(ns, arch, scheme):
     print(arch, scheme, "ok", logits[0, :3].tolist())
 
 
+def make_kat_multibranch(ns):
+    """The reference's un-frozen QuantAct on a (tensor, [scale per branch], [channels per branch]) input."""
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    for i, (bits, mode) in enumerate([(8, "symmetric"), (4, "asymmetric"), (8, "asymmetric")]):
+        act = ns.quant_modules.QuantAct(activation_bit=bits, quant_mode=mode)
+        scales = [torch.tensor([0.021]), torch.tensor([0.0173]), torch.tensor([0.05])]
+        chans = [3, 5, 2]
+        lo = 0 if mode == "asymmetric" else -100
+        x = torch.cat([torch.randint(lo, 100, (2, c, 4, 4), generator=g).float() * s for c, s in zip(chans, scales)], dim=1)
+        y, sf = act((x.clone(), [s.clone() for s in scales], chans))
+        out["mb_%d_x" % i] = x.numpy()
+        out["mb_%d_y" % i] = y.numpy()
+        out["mb_%d_sf" % i] = sf.view(-1).numpy()
+    out["specs"] = np.array(json.dumps([dict(bits=b, mode=m) for b, m in [(8, "symmetric"), (4, "asymmetric"), (8, "asymmetric")]]))
+    np.savez_compressed(os.path.join(HERE, "kat_multibranch.npz"), **out)
+    print("kat_multibranch ok")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     ns = rh.load()
+    if len(sys.argv) == 2 and sys.argv[1] == "--multibranch":  # QuantAct on concatenated branches (quant_modules.py:275-286)
+        make_kat_multibranch(ns)
+        sys.exit(0)
     if len(sys.argv) == 4 and sys.argv[1] == "--net":         # one extra network golden, e.g. --net resnet101 uniform8
         make_net(ns, sys.argv[2], sys.argv[3])
         sys.exit(0)
