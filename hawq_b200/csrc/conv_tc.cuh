@@ -415,6 +415,26 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
         }
       }
     } else if (tma_a) {
+      if constexpr (LEAN) {
+        // lean TMA producer: one lane of warp 0 chosen with elect.sync (straight-line UTMALDG / UBLKCP instead of an ELECT loop per
+        // issue), ring position tracked incrementally, the weight pointer of the channel block hoisted out of the k loop
+        if (warp == 0 && elect_one()) {
+          uint32_t stage = 0, phase = 0;
+          for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+            const int8_t* wsrc = p.w_tiled ? p.w_tiled + (size_t)(n0 / BN) * KT1 * S::B_STAGE : nullptr;
+            for (int kt = 0; kt < KT; ++kt) {
+              mbar_wait(empty_bar(stage), phase ^ 1);
+              const uint32_t a_base = smem_base + stage * S::STAGE;
+              mbar_arrive_expect_tx(full_bar(stage), S::A_STAGE + S::B_STAGE);
+              tma_load_2d(a_base, &maps.a, kt * 64, m0, full_bar(stage));
+              if (wsrc) bulk_load_1d(a_base + S::A_STAGE, wsrc + (size_t)kt * S::B_STAGE, S::B_STAGE, full_bar(stage));
+              else tma_load_2d(a_base + S::A_STAGE, &maps.b, kt * 64, n0, full_bar(stage));
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      } else
       if (tid == 0) {
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
           const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
