@@ -519,7 +519,13 @@ int hawq_stem_conv_i8(hawq_handle* h, int32_t N, int32_t H, int32_t W, const int
   if (N > 65535) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_stem_conv_i8: N > 65535");
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   const dim3 grid((Wo + STEM_TW - 1) / STEM_TW, (Ho + STEM_TH - 1) / STEM_TH, N);
-  stem_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const uint32_t*)w, chan, N, H, W, Ho, Wo, clamp_lo, clamp_hi, out);
+  static const bool persist = [] { const char* e = getenv("HAWQ_B200_STEM_PERSIST"); return e && e[0] == '1'; }();   // opt-in until validated
+  if (persist) {
+    const long long tiles = (long long)N * grid.x * grid.y;
+    const int ctas = (int)(tiles < 4LL * h->sm_count ? tiles : 4LL * h->sm_count);
+    stem_conv_kernel<true><<<ctas, 256, 0, (cudaStream_t)stream>>>(x, (const uint32_t*)w, chan, N, H, W, Ho, Wo, clamp_lo, clamp_hi, out);
+  } else
+  stem_conv_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const uint32_t*)w, chan, N, H, W, Ho, Wo, clamp_lo, clamp_hi, out);
   return launch_check("stem_conv");
 }
 
