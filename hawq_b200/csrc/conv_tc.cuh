@@ -263,7 +263,9 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // debug timeline: role 0 producer (warp 0), 1 MMA, 2 epilogue (first epilogue warp); 8 events x 64 tiles per role
   auto trace = [&](int role, uint32_t tile_i, int ev) {
-    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tile_i < 64) p.trace[(role * 64 + tile_i) * 8 + ev] = clock64();
+    if constexpr (!LEAN) {     // the lean variant carries no tracing code at all
+      if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tile_i < 64) p.trace[(role * 64 + tile_i) * 8 + ev] = clock64();
+    }
   };
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.Cout / BN;
   const int num_tiles = m_tiles * n_tiles;
