@@ -115,6 +115,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
   __trap();
 }
+// same, but the spin loop is not unrolled: ~8 instead of ~270 SASS instructions per call site (the unrolled form makes the kernels
+// 2x larger and shows up as instruction-fetch stalls); used by the LEAN variant
+__device__ __forceinline__ void mbar_wait_small(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < 4000000u; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
 // the mbarrier arrives (count not incremented) once all cp.async operations previously issued by this thread have landed
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -267,6 +275,10 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
       if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tile_i < 64) p.trace[(role * 64 + tile_i) * 8 + ev] = clock64();
     }
   };
+  auto kwait = [&](uint32_t bar, uint32_t parity) {
+    if constexpr (LEAN) mbar_wait_small(bar, parity);
+    else mbar_wait(bar, parity);
+  };
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.Cout / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int KT1 = p.KH * p.KW * p.cin_chunks;                 // k-tiles of the main convolution
@@ -355,7 +367,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
         const int h = rr / p.W, w = rr - h * p.W;
         for (int c = 0; c < chunks; ++c, ++g) {
           if (tid == 0 && g + 1 < total_g) issue_patch(g + 1);            // prefetch into the buffer freed one chunk ago
-          mbar_wait(patch_bar((int)(g & 1)), (uint32_t)((g >> 1) & 1));
+          kwait(patch_bar((int)(g & 1)), (uint32_t)((g >> 1) & 1));
           const uint8_t* patch = smem + S::PATCH_OFF + (g & 1) * S::PATCH_BUF;
 #pragma unroll 1
           for (int kh = 0; kh < 3; ++kh, it += 3) {
@@ -367,7 +379,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
               const int stage = (it + kw) % STAGES;
-              mbar_wait(empty_bar(stage), (((it + kw) / STAGES) & 1) ^ 1);
+              kwait(empty_bar(stage), (((it + kw) / STAGES) & 1) ^ 1);
               if (tid == 0) {                                            // weights of this k-tile: K index = tap * Cin + c * 64
                 const int ktile = (kh * 3 + kw) * chunks + c;
                 mbar_arrive_expect_tx(full_bar(stage), S::B_STAGE);
@@ -426,7 +438,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
             const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
             const int8_t* wsrc = p.w_tiled ? p.w_tiled + (size_t)(n0 / BN) * KT1 * S::B_STAGE : nullptr;
             for (int kt = 0; kt < KT; ++kt) {
-              mbar_wait(empty_bar(stage), phase ^ 1);
+              kwait(empty_bar(stage), phase ^ 1);
               const uint32_t a_base = smem_base + stage * S::STAGE;
               mbar_arrive_expect_tx(full_bar(stage), S::A_STAGE + S::B_STAGE);
               tma_load_2d(a_base, &maps.a, kt * 64, m0, full_bar(stage));
@@ -442,7 +454,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
           const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
           for (int kt = 0; kt < KT; ++kt, ++it) {
             const int stage = it % STAGES;
-            mbar_wait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
+            kwait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
             const uint32_t a_base = smem_base + stage * S::STAGE;
             mbar_arrive_expect_tx(full_bar(stage), S::A_STAGE + S::B_STAGE);
             tma_load_2d(a_base, &maps.a, kt * 64, m0, full_bar(stage));
@@ -475,7 +487,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
       if (warp == 0) trace(0, ptile, 0);
       for (int kt = 0; kt < KT; ++kt, ++it) {
         const int stage = it % STAGES;
-        mbar_wait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
+        kwait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
         if (warp == 0 && kt == 0) trace(0, ptile, 1);
         const uint32_t a_base = smem_base + stage * S::STAGE;
         const uint32_t b_base = a_base + S::A_STAGE;
@@ -549,12 +561,12 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
         uint32_t stage = 0, phase = 0, a_lo = a_lo0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
           const int buf = tile_iter & 1;
-          mbar_wait(tempty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);
+          kwait(tempty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem0 = tmem_base + buf * ACC_STRIDE;
           for (int kt = 0; kt < KT; ++kt) {
             const uint32_t d_tmem = d_tmem0 + ((DUAL && kt >= KT1) ? BN : 0);
-            mbar_wait(full_bar(stage), phase);
+            kwait(full_bar(stage), phase);
             if (consumer_fence) fence_proxy_async();
             tc_fence_after();
             const uint32_t b_lo = a_lo + (S::A_STAGE >> 4);
@@ -572,14 +584,14 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
         const int buf = tile_iter & 1;
         trace(1, tile_iter, 0);
-        mbar_wait(tempty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        kwait(tempty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         trace(1, tile_iter, 1);
         const uint32_t d_tmem0 = tmem_base + buf * ACC_STRIDE;
         for (int kt = 0; kt < KT; ++kt, ++it) {
           const uint32_t d_tmem = d_tmem0 + ((DUAL && kt >= KT1) ? BN : 0);     // dual mode: identity conv -> second accumulator
           const int stage = it % STAGES;
-          mbar_wait(full_bar(stage), (it / STAGES) & 1);
+          kwait(full_bar(stage), (it / STAGES) & 1);
           fence_proxy_async();            // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
           tc_fence_after();
           if (kt == 0) trace(1, tile_iter, 2);
@@ -708,11 +720,11 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
       }
 
       if (ew == 0) trace(2, tile_iter, 0);
-      mbar_wait(tfull_bar(buf), (tile_iter >> 1) & 1);
+      kwait(tfull_bar(buf), (tile_iter >> 1) & 1);
       tc_fence_after();
       if (ew == 0) trace(2, tile_iter, 1);
       if constexpr (EPI == TC_EPI_RES22) {
-        mbar_wait(res_bar(ew, tile_iter & 1), (tile_iter >> 1) & 1);     // residual tile landed (TMA)
+        kwait(res_bar(ew, tile_iter & 1), (tile_iter >> 1) & 1);     // residual tile landed (TMA)
         if (lane == 0) bulk_wait_read_all();                            // previous tile's TMA stores have read y / low tiles
       } else if constexpr (DUAL) {
         if (lane == 0) bulk_wait_read_all();                            // previous tile's TMA stores have read y / low tiles
