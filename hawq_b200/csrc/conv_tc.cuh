@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
     }
   };
   auto kwait = [&](uint32_t bar, uint32_t parity) {
-    if constexpr (LEAN) mbar_wait_small(bar, parity);
+    if constexpr (LEAN || EW == 16) mbar_wait_small(bar, parity);     // the opt-in variants
     else mbar_wait(bar, parity);
   };
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.Cout / BN;
