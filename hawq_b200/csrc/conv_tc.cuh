@@ -279,6 +279,12 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
     if constexpr (LEAN || EW == 16) mbar_wait_small(bar, parity);     // the opt-in variants
     else mbar_wait(bar, parity);
   };
+  // the thread that issues TMA / bulk copies on behalf of the producers: thread 0, or (LEAN) a lane of warp 0 picked with elect.sync so
+  // that nvcc emits the issue straight-line (see the MMA issuer)
+  auto tma_issuer = [&]() -> bool {
+    if constexpr (LEAN) return warp == 0 && elect_one() != 0;
+    else return tid == 0;
+  };
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.Cout / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int KT1 = p.KH * p.KW * p.cin_chunks;                 // k-tiles of the main convolution
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
         mbar_arrive_expect_tx(patch_bar((int)(g & 1)), patch_bytes);
         tma_load_2d(smem_base + S::PATCH_OFF + (uint32_t)(g & 1) * S::PATCH_BUF, &maps.patch, c * PROWB, m0 - p.W - 1, patch_bar((int)(g & 1)));
       };
-      if (tid == 0 && total_g > 0) issue_patch(0);
+      if (total_g > 0 && tma_issuer()) issue_patch(0);
       long long g = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
         const int rr = mm % (p.H * p.W);
         const int h = rr / p.W, w = rr - h * p.W;
         for (int c = 0; c < chunks; ++c, ++g) {
-          if (tid == 0 && g + 1 < total_g) issue_patch(g + 1);            // prefetch into the buffer freed one chunk ago
+          if (g + 1 < total_g && tma_issuer()) issue_patch(g + 1);        // prefetch into the buffer freed one chunk ago
           kwait(patch_bar((int)(g & 1)), (uint32_t)((g >> 1) & 1));
           const uint8_t* patch = smem + S::PATCH_OFF + (g & 1) * S::PATCH_BUF;
 #pragma unroll 1
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
             for (int kw = 0; kw < 3; ++kw) {
               const int stage = (it + kw) % STAGES;
               kwait(empty_bar(stage), (((it + kw) / STAGES) & 1) ^ 1);
-              if (tid == 0) {                                            // weights of this k-tile: K index = tap * Cin + c * 64
+              if (tma_issuer()) {                                        // weights of this k-tile: K index = tap * Cin + c * 64
                 const int ktile = (kh * 3 + kw) * chunks + c;
                 mbar_arrive_expect_tx(full_bar(stage), S::B_STAGE);
                 if (p.w_tiled) bulk_load_1d(smem_base + stage * S::STAGE + S::A_STAGE, p.w_tiled + ((size_t)(n0 / BN) * KT1 + ktile) * S::B_STAGE, S::B_STAGE, full_bar(stage));
@@ -506,7 +512,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
           if constexpr (!A4) cp_async_16(a_base + swz<64>(row, a_ch), src, v ? 16 : 0);
           else cp_async_16(smem_base + S::STG_OFF + (it % (LAG + 1)) * S::STG_SLOT + row * 32 + a_ch * 16, src, v ? 16 : 0);
         }
-        if (tid == 0) {                         // weights: one TMA box (64 x BN, SWIZZLE_64B) per k-tile
+        if (tma_issuer()) {                     // weights: one TMA box (64 x BN, SWIZZLE_64B) per k-tile
           mbar_arrive_expect_tx(full_bar(stage), S::B_STAGE);
           if (DUAL && kt >= KT1) bulk_load_1d(b_base, p.w2_tiled + ((size_t)(n0 / BN) * p.cin_chunks2 + (kt - KT1)) * S::B_STAGE, S::B_STAGE, full_bar(stage));
           else if (p.w_tiled) bulk_load_1d(b_base, p.w_tiled + ((size_t)(n0 / BN) * KT1 + kt) * S::B_STAGE, S::B_STAGE, full_bar(stage));
