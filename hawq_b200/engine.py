@@ -56,8 +56,11 @@ class CompiledModel:
             self._build(residual_bits)
 
     # -- one eager forward on the current stream
-    def _forward(self, bits):
-        qtensor.config.residual_bits = bits
+    def _forward(self, bits, fast=True):
+        with qtensor.engine_mode(residual_bits=bits, fast_kernels=fast, checked=True):
+            return self._forward_checked()
+
+    def _forward_checked(self):
         x = self.static_in
         if self.u8_input:
             act = self.model.quant_input
@@ -67,20 +70,19 @@ class CompiledModel:
         elif self.int_input:
             n, h, w, c = x.shape
             x = IntActivation(Node("int", (n, c, h, w), data=x.view(-1), bits=8, signed=True), self.device)
-        out = self.model(x)
-        qtensor.config.residual_bits = 32
-        return out
+        return self.model(x)
 
     def _build(self, bits, key=None):
         key = bits if key is None else key
+        fast = key != "safe"                    # "safe": no ratio promises -> saturating generic kernels
         idx = self.device.index
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             before = ops.launch_count
-            out = self._forward(bits)                  # warm-up: builds all parameter caches
+            out = self._forward(bits, fast)            # warm-up: builds all parameter caches
             self.launches[key] = ops.launch_count - before
-            self._forward(bits)
+            self._forward(bits, fast)
         # keep every module's plan (device-resident weights / per-channel parameters) alive for as long as graphs captured
         # here may replay, even if the modules drop or rebuild theirs (unfix(), load_state_dict)
         self._plans = getattr(self, "_plans", [])
@@ -95,7 +97,7 @@ class CompiledModel:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             ops.reset_status(idx)
-            out = self._forward(bits)
+            out = self._forward(bits, fast)
             ops.copy_status(idx, self.flag)
         self.graphs[key] = g
         self.outs[key] = out
@@ -105,7 +107,7 @@ class CompiledModel:
             self.graphs[key].replay()
         else:
             ops.reset_status(self.device.index)
-            self.outs[key] = self._forward(self.bits_of[key])
+            self.outs[key] = self._forward(self.bits_of[key], key != "safe")
             ops.copy_status(self.device.index, self.flag)
         return self.outs[key]
 
@@ -123,14 +125,10 @@ class CompiledModel:
             raise RuntimeError("hawq_b200: HAWQ_FLAG_BAD_RATIO raised (a dyadic ratio > 1 reached the fast kernel): results invalid")
         if flags & 4:                          # a ratio > 1 term left int32 on the fast path: saturating generic kernels
             self.fallbacks += 1
-            ops.fast_kernels = False
-            try:
-                with torch.no_grad():
-                    if "safe" not in self.outs:
-                        self._build(32, key="safe")
-                    out = self._run("safe")
-            finally:
-                ops.fast_kernels = True
+            with torch.no_grad():
+                if "safe" not in self.outs:
+                    self._build(32, key="safe")
+                out = self._run("safe")
             return out
         if self.residual_bits == 16 and flags & 1:
             self.fallbacks += 1

@@ -32,6 +32,15 @@ def _check_mode(mode):
         raise ValueError("unknown quant mode: {}".format(mode))
 
 
+_generation = [0]
+
+
+def _next_generation():
+    """Monotonic counter for cache keys of installed overrides (never reused, unlike id())."""
+    _generation[0] += 1
+    return _generation[0]
+
+
 def _drop_plan(module):
     """unfix(): the device-resident integer plan is rebuilt on the next frozen forward (SURVEY.md 8(b) lifecycle)."""
     module.__dict__.pop("_hawq_cache", None)
@@ -73,10 +82,12 @@ class QuantAct(Module):
     def unfix(self):
         self.running_stat = True
         self.fix_flag = False
+        self.load_frozen_scale(None)      # a stored scale belongs to the frozen plan: ranges calibrated from here on take over
 
     def load_frozen_scale(self, scale):
         """Use a stored ``act_scaling_factor`` (quantized_checkpoint.pth.tar) instead of the scale implied by x_min / x_max;
         ``None`` returns to the range buffers."""
+        self.__dict__["_override_gen"] = _next_generation()
         if scale is None:
             self.__dict__.pop("_scale_override", None)
             return
@@ -160,9 +171,10 @@ class QuantAct(Module):
 
 
 class _WeightQuantMixin:
-    def load_frozen_integers(self, w_sf, w_int, b_int=None):
+    def load_frozen_integers(self, w_sf, w_int=None, b_int=None):
         """Use stored integers (``weight_integer`` in the float weights' layout, per-channel scale, optional 32-bit
         ``bias_integer``) instead of deriving them from the float parameters; ``w_sf=None`` returns to the float parameters."""
+        self.__dict__["_override_gen"] = _next_generation()
         if w_sf is None:
             self.__dict__.pop("_frozen_integers", None)
             return
@@ -191,8 +203,11 @@ class _WeightQuantMixin:
         w2 = w.data.contiguous().view(w.shape[0], -1)
         if self.per_channel:
             lo, hi = qmath.per_channel_minmax(w2, percentile)
-        else:
+        elif percentile == 0:
             lo, hi = w.data.min().expand(1), w.data.max().expand(1)
+        else:                                    # per-tensor percentile range: get_percentile_min_max (quant_utils.py:40-70)
+            lo, hi = qmath.percentile_minmax(w.data.reshape(-1), 100 - percentile, percentile)
+            lo, hi = lo.expand(1), hi.expand(1)
         w_sf = qmath.symmetric_scale(self.weight_bit, lo, hi, self.per_channel)
         w_int = qmath.quantize(w, self.weight_bit, w_sf)
         bias_sf = w_sf.view(1, -1) * pre_act_sf.view(1, -1)
@@ -242,6 +257,7 @@ class QuantBnConv2d(Module, _WeightQuantMixin):
         self.fix_flag = False
         self.fix_BN = self.training_BN_mode
         _drop_plan(self)
+        self.load_frozen_integers(None)   # stored integers belong to the frozen plan; new float weights take over
 
     def integer_params(self, pre_act_scaling_factor):
         """(w_sf[C], weight_integer OIHW, bias_integer[C], bias_sf[1,C]) of the folded-BN branch; also refreshes the
@@ -321,6 +337,7 @@ class QuantConv2d(Module, _WeightQuantMixin):
     def unfix(self):
         self.fix_flag = False
         _drop_plan(self)
+        self.load_frozen_integers(None)   # stored integers belong to the frozen plan; new float weights take over
 
     def integer_params(self, pre_act_scaling_factor):
         w_sf, w_int, b_int, bias_sf = self._weight_params(self.weight, self.bias, pre_act_scaling_factor,
@@ -374,6 +391,7 @@ class QuantLinear(Module, _WeightQuantMixin):
     def unfix(self):
         self.fix_flag = False
         _drop_plan(self)
+        self.load_frozen_integers(None)   # stored integers belong to the frozen plan; new float weights take over
 
     def integer_params(self, prev_act_scaling_factor):
         w_sf, w_int, b_int, bias_sf = self._weight_params(self.weight, self.bias, prev_act_scaling_factor, 0)

@@ -113,14 +113,10 @@ def epilogue(mode, relu=0, out_bits=0, clamp=(0, 0), res_kind=0, res_bits=0, res
                               y_bits, low_bits, low_me[0], low_me[1], low_clamp[0], low_clamp[1], cout_store, flags)
 
 
-fast_kernels = True   # set False to withhold the HAWQ_EP_* promises (always-saturating generic kernels)
-
-
 def ratio_flags(*pairs):
     """HAWQ_EP_RATIOS_* promise for a set of (m, e) pairs (or (m list, e list)): LE_ONE when every ratio m * 2^-e <= 1
-    (e >= 31 or m == 0), LE_2P20 when every ratio <= 2^20 (e >= 11), else 0."""
-    if not fast_kernels:
-        return 0
+    (e >= 31 or m == 0), LE_2P20 when every ratio <= 2^20 (e >= 11), else 0.  (Whether the promise is made at all is the
+    caller's execution mode: qtensor.EngineConfig.)"""
     min_e = 99
     for m, e in pairs:
         ms = m if isinstance(m, (list, tuple)) else [m]

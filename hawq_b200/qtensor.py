@@ -13,23 +13,55 @@ unit's low-bit activation) folded into the kernel epilogue.
 ``nn.ReLU``, ``nn.MaxPool2d``, ``+``, ``.view`` on an ``IntActivation`` are intercepted through
 ``__torch_function__`` and recorded on the node; anything else is not an integer-path operation and raises.
 """
-import numpy as np
+import contextlib
 import os
+import threading
+
+import numpy as np
 
 import torch
 
 from . import ops, quant_math as qmath
-from ._lib import EPI_RAW_I32, EPI_REQUANT, EPI_RESIDUAL, ERR_UNSUPPORTED, HawqError
+from ._lib import EPI_RAW_I32, EPI_REQUANT, EPI_RESIDUAL, EP_RATIOS_LE_2P20, ERR_UNSUPPORTED, HawqError
 
 
-class EngineConfig:
-    """residual_bits: storage of the post-ReLU residual stream: 32 (always exact) or 16 (uint16 + sticky overflow
-    flag HAWQ_FLAG_RESIDUAL_OVERFLOW; ``CompiledModel`` re-runs in 32-bit mode when the flag is raised)."""
+class EngineConfig(threading.local):
+    """Per-thread execution mode of the frozen forward (no process-global state: several engines / threads may run at once).
+
+    residual_bits: storage of the post-ReLU residual stream: 32 (always exact) or 16 (uint16 + sticky overflow flag
+        HAWQ_FLAG_RESIDUAL_OVERFLOW; ``CompiledModel`` re-runs in 32-bit mode when the flag is raised).
+    fast_kernels: False withholds every HAWQ_EP_RATIOS_* promise (always-saturating generic kernels).
+    checked: True when the caller reads the device status word after the forward (``CompiledModel`` does).  The plain eager
+        frozen forward does not, so it never promises HAWQ_EP_RATIOS_LE_2P20: the WIDE kernels only *flag* an int32 overflow and
+        rely on the host to re-run, whereas ratios <= 1 cannot overflow and the generic kernels saturate like the reference."""
     residual_bits = 32
+    fast_kernels = True
+    checked = False
     dual = os.environ.get("HAWQ_B200_DUAL", "1") != "0"   # resize units: identity conv + last conv in one kernel (uint16 stream only)
 
 
 config = EngineConfig()
+
+
+@contextlib.contextmanager
+def engine_mode(residual_bits=32, fast_kernels=True, checked=False):
+    """Scoped execution mode (restored on exit, also when the forward raises)."""
+    saved = (config.residual_bits, config.fast_kernels, config.checked)
+    config.residual_bits, config.fast_kernels, config.checked = residual_bits, fast_kernels, checked
+    try:
+        yield config
+    finally:
+        config.residual_bits, config.fast_kernels, config.checked = saved
+
+
+def _ratio_flags(*pairs):
+    """HAWQ_EP_RATIOS_* promise for this thread's execution mode (see EngineConfig)."""
+    if not config.fast_kernels:
+        return 0
+    f = ops.ratio_flags(*pairs)
+    if f == EP_RATIOS_LE_2P20 and not config.checked:
+        return 0
+    return f
 
 
 class Node:
@@ -132,6 +164,10 @@ def _key(t):
     return None if t is None else _cpu_f32(t).numpy().tobytes()
 
 
+def _buf_key(t):
+    return None if t is None else (id(t), t._version, t.data_ptr())
+
+
 def _dev_of(x):
     return x.device
 
@@ -153,7 +189,9 @@ def _act_clamp(act):
 def _frozen_scale(act):
     """Scale of a frozen QuantAct, CPU fp32 [1]; refreshes the act_scaling_factor buffer like the reference forward."""
     c = act.__dict__.setdefault("_hawq_cache", {})
-    key = ("scale", _key(act.x_min), _key(act.x_max), act.activation_bit, act.quant_mode, id(act.__dict__.get("_scale_override")))
+    # keyed on buffer identity + in-place version (no device->host copy on a hit: the buffers may live on the GPU and
+    # this runs inside CUDA-graph capture); `x_min += lo` bumps _version, `x_min = ...` rebinds the buffer
+    key = ("scale", _buf_key(act.x_min), _buf_key(act.x_max), act.activation_bit, act.quant_mode, act.__dict__.get("_override_gen", 0))
     if c.get("scale_key") != key:
         sf = act.current_scale().detach().to("cpu", torch.float32).reshape(1)
         c["scale_key"], c["scale"] = key, sf
@@ -195,7 +233,7 @@ def _param_versions(mod):
         if name.rsplit(".", 1)[-1] in _OWN_BUFFERS or "num_batches_tracked" in name:
             continue
         vs.append((id(t), t._version))
-    vs.append(id(mod.__dict__.get("_frozen_integers")))      # integers installed from a quantized checkpoint
+    vs.append(mod.__dict__.get("_override_gen", 0))          # integers installed from a quantized checkpoint
     return tuple(vs)
 
 
@@ -334,7 +372,7 @@ def _conv_case0(n, act, device):
     lo, hi = _act_clamp(act)
     out = _alloc(device, nb * ho * wo * ent["cout"], bits)
     ep = ops.epilogue(EPI_REQUANT, relu=n.relu, out_bits=bits, clamp=(lo, hi),
-                      flags=ops.ratio_flags((m, e)))
+                      flags=_ratio_flags((m, e)))
     _launch_conv(n, ent, ep, chan, device, out=out)
     return Node("int", (nb, ent["cout"], ho, wo), data=out, bits=bits, signed=(act.quant_mode == "symmetric"))
 
@@ -346,7 +384,7 @@ def _conv_raw(n, device):
     chan = _chan_tensor(ent, "raw", [0] * ent["cout"], [1] * ent["cout"], device)
     nb, _, _, ho, wo = _conv_out_hw(n, ent)
     out = _alloc(device, nb * ho * wo * ent["cout"], 32)
-    _launch_conv(n, ent, ops.epilogue(EPI_RAW_I32, flags=ops.ratio_flags()), chan, device, out=out)
+    _launch_conv(n, ent, ops.epilogue(EPI_RAW_I32, flags=_ratio_flags()), chan, device, out=out)
     return out, ent
 
 
@@ -400,7 +438,7 @@ def _launch_residual(r, low_act, device):
         low_node = Node("int", (nb, ent["cout"], ho, wo), data=low, bits=low_act.activation_bit,
                         signed=(low_act.quant_mode == "symmetric"))
     ep = ops.epilogue(EPI_RESIDUAL, relu=r.relu, res_kind=res_kind, res_bits=res_bits, res_me=res_me, y_bits=y_bits,
-                      flags=ops.ratio_flags(*pairs), **kw)
+                      flags=_ratio_flags(*pairs), **kw)
     if dual is not None and ep.flags == 0:       # no ratio promise (saturating generic kernels): two launches
         res, _ = _conv_raw(ident, device)
         dual = None

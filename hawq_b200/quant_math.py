@@ -75,6 +75,16 @@ def per_channel_minmax(w2d, percentile=0):
     return torch.kthvalue(w2d, k=lo_idx, dim=1).values, torch.kthvalue(w2d, k=hi_idx, dim=1).values
 
 
+def percentile_minmax(flat, lower_percentile, upper_percentile):
+    """get_percentile_min_max (quant_utils.py:40-70) on a 1-D tensor, tensors out."""
+    n = flat.shape[0]
+    lower_index = round(n * (1 - lower_percentile * 0.01))
+    upper_index = round(n * upper_percentile * 0.01)
+    hi = torch.kthvalue(flat, k=upper_index).values
+    lo = hi * 0 if lower_percentile == 0 else -torch.kthvalue(-flat, k=lower_index).values
+    return lo, hi
+
+
 def requant_ratio(a_sf, w_sf, out_sf):
     """fp64(fp32(fp64(a)*fp64(w))) / fp64(fp32(out))   (quant_utils.py:394-397)."""
     prod = a_sf.type(torch.double) * w_sf.type(torch.double)
@@ -99,9 +109,10 @@ def _rs(t, z):
 def _float_requant(z_int, a_sf, w_sf, out_sf, z):
     import numpy as np
     ratio = _rs(requant_ratio(a_sf, w_sf, out_sf), z)
-    mant, ex = np.frexp(ratio.reshape(-1).numpy())
-    m = torch.tensor([math.floor(v * 2.0 ** 31 + 0.5) for v in mant.tolist()], dtype=torch.double).view(ratio.shape)
-    e = torch.from_numpy(31.0 - ex).view(ratio.shape)
+    # batch_frexp goes through the host (quant_utils.py:202: `.cpu().numpy()`) and returns tensors on the data's device
+    mant, ex = np.frexp(ratio.detach().reshape(-1).cpu().double().numpy())
+    m = torch.tensor([math.floor(v * 2.0 ** 31 + 0.5) for v in mant.tolist()], dtype=torch.double).view(ratio.shape).to(z_int.device)
+    e = torch.from_numpy(31.0 - ex).view(ratio.shape).to(z_int.device)
     return torch.round(z_int.type(torch.double) * m / (2.0 ** e))
 
 
