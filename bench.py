@@ -131,7 +131,7 @@ def usable_cpus(cap=32):
     return max(1, min(n, cap))
 
 
-def cpu_forward_rate(arch, scheme, max_batch, steps, warmup, budget_s=25.0):
+def cpu_forward_rate(arch, scheme, max_batch, steps, warmup, budget_s=25.0, fixed_batch=False):
     """The reference's fake-quant forward (oracle/fakequant.py restatement, pinned bit-exact to the unmodified reference)
     on the usable host cores.  The per-step sample (images per forward) is sized from a 1-image probe so that `steps` timed
     forwards fit in about `budget_s` seconds.  Returns (images/s, threads, seconds per step, images per step)."""
@@ -149,8 +149,12 @@ def cpu_forward_rate(arch, scheme, max_batch, steps, warmup, budget_s=25.0):
     t0 = time.perf_counter()
     m(x1)
     per_img = time.perf_counter() - t0
-    steps = max(1, min(steps, int(4 * budget_s / max(per_img, 1e-6))))   # a pathologically slow host: fewer steps rather than minutes
-    batch = int(max(1, min(max_batch, budget_s / max(steps, 1) / max(per_img, 1e-6))))
+    if fixed_batch:      # every step is a full batch of the workload; the budget bounds the number of steps (>= 1)
+        batch = max_batch
+        steps = max(1, min(steps, int(budget_s / max(per_img * batch * 0.8, 1e-6)) - 1))
+    else:
+        steps = max(1, min(steps, int(4 * budget_s / max(per_img, 1e-6))))   # a pathologically slow host: fewer steps rather than minutes
+        batch = int(max(1, min(max_batch, budget_s / max(steps, 1) / max(per_img, 1e-6))))
     x = synthetic_batch(batch, 1)
     for _ in range(min(warmup, 1)):
         m(x)
@@ -164,23 +168,34 @@ def cpu_forward_rate(arch, scheme, max_batch, steps, warmup, budget_s=25.0):
 
 
 def run_reference(a):
+    """The reference's CPU path on this box's host cores, on OUR arm's workload: every step is one forward of a.batch images
+    (the configuration our JSON line names).  The number of timed steps is bounded by a time budget (a batch-128 ResNet-50
+    forward takes ~13 s on 16 cores), and the line says how many ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = max(1, a.steps)
     warm = max(1, a.warmup)
-    ips, threads, sec, cpu_b, steps = cpu_forward_rate(a.arch, a.scheme, a.cpu_batch, steps, warm, budget_s=60.0)
-    line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": a.gpus, "steps": steps, "warmup": warm,
+    ips, threads, sec, cpu_b, steps = cpu_forward_rate(a.arch, a.scheme, a.batch, steps, warm, budget_s=120.0, fixed_batch=True)
+    line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": a.gpus, "steps": steps, "warmup": 1,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32 emulating int8/int4 (reference fake-quant)", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "%s_%s_b%d" % (a.arch, a.scheme, a.batch), "arch": a.arch, "bit_config": a.scheme,
-                       "batch_per_gpu": a.batch, "input": "synthetic 224x224"},
+            "config": workload_config(a, 1, None),
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                             "sample": "%d steps, each the forward of %d image(s) of the workload, through oracle/fakequant.py (torch CPU restatement of the "
-                                       "reference forward, bit-exact vs the unmodified reference in the build container)" % (steps, cpu_b)},
+                             "sample": "%d timed step(s) (of the %d requested: bounded by a 120 s budget), each the forward of %d images, through oracle/fakequant.py "
+                                       "(torch CPU restatement of the reference forward, bit-exact vs the unmodified reference in the build container)"
+                                       % (steps, max(1, a.steps), cpu_b)},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def workload_config(a, world, detail):
+    """`config` of the JSON line; identical keys for both arms (the reference arm runs the same workload on the host cores)."""
+    B = a.batch
+    return {"workload": "%s_%s_b%d" % (a.arch, a.scheme, B), "arch": a.arch, "bit_config": a.scheme, "batch_per_gpu": B,
+            "global_batch": B * world, "input": "synthetic int8 NHWC 224x224x3",
+            "parallelism": "dp%d (batch sharded, logits all-gather)" % world if world > 1 else "single GPU"}
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -213,14 +228,11 @@ def run_ours(a):
     host_pool = [torch.clamp(torch.round(torch.randn(B, 224, 224, 3, generator=g) / s_in), -128, 127).to(torch.int8).pin_memory()
                  for _ in range(POOL)]
     dev_pool = [t.to(dev) for t in host_pool]
-    eng = hb.compile_model(q, dev_pool[0], residual_bits=a.residual_bits)
-    gathered = None
+    # N > 1: the one collective of the path (all-gather of the logits, BASELINE config 5) is captured inside the CUDA graph
+    eng = hb.compile_model(q, dev_pool[0], residual_bits=a.residual_bits, gather=(world > 1))
 
     def step(i, src):
-        out = eng.run_async(src[i % POOL])
-        if world > 1:
-            return hb.all_gather_logits(out)
-        return out
+        return eng.run_async(src[i % POOL])
 
     def barrier():
         if world > 1:
@@ -250,14 +262,15 @@ def run_ours(a):
     def batches(n):
         for i in range(n):
             yield host_pool[i % POOL]
-    post = hb.all_gather_logits if world > 1 else None
-    for _ in eng.run_pipelined(batches(3), post=post):
+    # (N > 1: the gathered logits stay on the device, as the consumer of a sharded batch would use them; the host reads this
+    # rank's shard of the result)
+    for _ in eng.run_pipelined(batches(3)):
         pass
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     checksum = 0.0
-    for res in eng.run_pipelined(batches(a.steps), post=post):
+    for res in eng.run_pipelined(batches(a.steps)):
         checksum += float(res[0, 0])                   # the host really consumes every result
     f1.record()
     barrier()
@@ -269,10 +282,15 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
+    # ---- parity of the timed configuration: the logits of one timed batch (CUDA graph, uint16 stream, fused kernels) against an
+    # eager run of the same batch on the int32 residual stream without ratio promises (generic saturating kernels)
+    parity = None
+    if rank == 0:
+        parity = parity_check(hb, q, eng, dev_pool[0])
     # ---- roofline leg: per-launch CUDA-event timing of an eager (un-graphed) pass, same stream, same buffers
     roof, detail = None, None
     if rank == 0 and not a.no_roofline:
-        roof, detail = roofline_leg(hb, ops, q, dev_pool, a)
+        roof, detail = roofline_leg(hb, ops, q, dev_pool, a, ms / a.steps)
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
         ips, threads, sec, cpu_b, _ = cpu_forward_rate(a.arch, a.scheme, a.cpu_batch, 3, 1, budget_s=20.0)
@@ -287,21 +305,19 @@ def run_ours(a):
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int8" if a.scheme == "uniform8" else ("int4 storage / int8 MMA" if a.scheme == "uniform4" else "mixed int4/int8"),
                 "data": "synthetic",
-                "config": {"workload": "%s_%s_b%d" % (a.arch, a.scheme, B), "arch": a.arch, "bit_config": a.scheme, "batch_per_gpu": B,
-                           "global_batch": B * world, "input": "synthetic int8 NHWC 224x224x3, %d rotating batches" % POOL,
-                           "parallelism": "dp%d (batch sharded, logits all-gather)" % world if world > 1 else "single GPU",
-                           "l2": ("per-step working set (%.1f GB of activations) exceeds the 126 MB L2; inputs rotate" % (detail["act_bytes"] / 1e9)) if detail
-                                 else "per-step working set (GBs of activations at batch 128) exceeds the 126 MB L2; inputs rotate",
-                           "residual_stream": "uint%d" % a.residual_bits if a.residual_bits == 16 else "int32", "cuda_graph": True,
-                           "overflow_flag_seen": bool(flag & 1)},
+                "config": dict(workload_config(a, world, detail),
+                               l2=("per-step working set (%.1f GB of activations) exceeds the 126 MB L2; %d input batches rotate" % (detail["act_bytes"] / 1e9, POOL)) if detail and detail["act_bytes"] > 2.5e8
+                               else "%d input batches rotate; at this batch size the per-step working set is L2-resident (latency-bound regime)" % POOL,
+                               residual_stream="uint%d" % a.residual_bits if a.residual_bits == 16 else "int32", cuda_graph=True,
+                               overflow_flag_seen=bool(flag & 1)),
                 "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(host_pool[0].numel()),
-                        "d2h_bytes_per_step": int(B * world * 1000 * 4 + 4), "ms_per_step": ms_e2e / a.steps,
+                        "d2h_bytes_per_step": int(B * 1000 * 4 + 4), "ms_per_step": ms_e2e / a.steps,
                         "int32_fallbacks": eng.fallbacks},
                 "gpu_launches": eng.gpu_launches * a.steps,
                 "clocks": clk,
                 "tensor": {"achieved_tops": 2 * macs * value / 1e12, "nominal_int8_peak_tops": INT8_TC_PEAK_OPS / 1e12,
                            "frac_of_nominal": 2 * macs * value / INT8_TC_PEAK_OPS},
-                "roofline": roof, "cpu_baseline": cpu}
+                "parity": parity, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line))
         if a.detail and detail is not None:
             with open(a.detail, "w") as f:
@@ -310,8 +326,33 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def roofline_leg(hb, ops, q, dev_pool, a):
-    """Eager pass with a CUDA event pair around every launch (torch current stream = the launching stream)."""
+def parity_check(hb, q, eng, x):
+    """Logits of one timed batch through the benchmarked path vs an eager (un-graphed) run of the same batch with int32
+    residuals and no ratio promises.  Two independent kernel sets (fused tcgen05 / generic IMMA) must agree bit for bit."""
+    from hawq_b200 import qtensor
+    from hawq_b200.qtensor import IntActivation, Node
+    fast = eng(x).clone()
+    n, h, w, c = x.shape
+    with torch.no_grad(), qtensor.engine_mode(residual_bits=32, fast_kernels=False, checked=False):
+        ref = q(IntActivation(Node("int", (n, c, h, w), data=x.view(-1), bits=8, signed=True), x.device))
+    torch.cuda.synchronize()
+    return {"what": "all %d x %d logits of one timed batch: benchmarked path (CUDA graph, fused tcgen05 kernels, uint16 stream) vs eager generic "
+                    "kernels on the int32 stream" % tuple(fast.shape),
+            "bit_equal": bool(torch.equal(fast, ref)), "rows_checked": int(fast.shape[0])}
+
+
+def build_digest():
+    from hawq_b200.build import OUT
+    try:
+        return open(OUT + ".stamp").read().strip()[:16]
+    except OSError:
+        return None
+
+
+def roofline_leg(hb, ops, q, dev_pool, a, graph_ms_per_step):
+    """Per-launch CUDA-event timing of an eager pass (torch current stream = the launching stream) gives every kernel's SHARE of
+    the step; the denominator of `achieved` is the graph-timed step of the timed region x that share (the eager event sum exceeds
+    the graph-timed step: no PDL overlap, event gaps)."""
     from hawq_b200 import qtensor
     from hawq_b200.qtensor import IntActivation, Node
     peak, which, _ = measured_peaks()
@@ -319,12 +360,10 @@ def roofline_leg(hb, ops, q, dev_pool, a):
     rows = {}
     for r in range(reps + 1):
         ops.timer = [] if r > 0 else None
-        qtensor.config.residual_bits = a.residual_bits
         x = dev_pool[r % len(dev_pool)]
         n, h, w, c = x.shape
-        with torch.no_grad():
+        with torch.no_grad(), qtensor.engine_mode(residual_bits=a.residual_bits, checked=True):
             q(IntActivation(Node("int", (n, c, h, w), data=x.view(-1), bits=8, signed=True), x.device))
-        qtensor.config.residual_bits = 32
         torch.cuda.synchronize()
         if r > 0:
             for i, (name, info, e0, e1) in enumerate(ops.timer):
@@ -340,34 +379,44 @@ def roofline_leg(hb, ops, q, dev_pool, a):
         g = agg.setdefault(r["kernel"], {"ms": 0.0, "bytes": 0, "macs": 0, "launches": 0})
         g["ms"] += ms; g["bytes"] += r["bytes"]; g["macs"] += r["macs"]; g["launches"] += 1
     total_ms = sum(g["ms"] for g in agg.values())
-    # the dominant kernel is conv_tc_kernel: every hawq_conv2d / hawq_conv2d_dual launch instantiates the same template
+    scale = graph_ms_per_step / total_ms             # eager event time -> time inside the graph-timed step
+    # kernel families: conv_tc (+ its dual-accumulator instantiation) is one template; conv_halo is the in-place 3x3 kernel
     fam = {}
     for k, g in agg.items():
-        f = fam.setdefault("conv_tc_kernel" if k.startswith("hawq_conv2d") else k, {"ms": 0.0, "bytes": 0, "macs": 0, "launches": 0})
+        f = fam.setdefault("conv_tc_kernel" if k.startswith("conv_tc") else ("conv_halo_kernel" if k == "conv_halo" else k),
+                           {"ms": 0.0, "bytes": 0, "macs": 0, "launches": 0})
         for key in f:
             f[key] += g[key]
     top = max(fam, key=lambda k: fam[k]["ms"])
     t = fam[top]
-    achieved = t["bytes"] / (t["ms"] / 1e3) / 1e9
-    # measured DRAM traffic of the same kernel family: not measurable live (needs ncu); taken from the committed summary of
-    # the ncu pass over this very command (tools/summarize_ncu.py -> profiles/ncu_traffic.json), null if there is none
+    achieved = t["bytes"] / (t["ms"] * scale / 1e3) / 1e9
+    # measured DRAM traffic of that kernel: from the ncu pass over this command with THIS build (tools/summarize_ncu.py writes the
+    # build digest next to the numbers); a stale or missing entry gives null
     traffic = None
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             ent = json.load(f).get("%s:%s:%d" % (a.arch, a.scheme, a.batch))
-        if ent and top == "conv_tc_kernel":
-            traffic = ent["traffic_bytes_per_launch"]
+        if ent and ent.get("build") == build_digest() and top in ent.get("kernels", {}):
+            traffic = ent["kernels"][top]["traffic_bytes_per_launch"]
     except (OSError, ValueError, KeyError):
         traffic = None
+    families = {k: {"launches_per_step": v["launches"], "share_of_step": v["ms"] / total_ms, "ms_in_step": v["ms"] * scale,
+                    "algorithmic_GBps": v["bytes"] / (v["ms"] * scale / 1e3) / 1e9, "frac_of_hbm_peak": v["bytes"] / (v["ms"] * scale / 1e3) / 1e9 / peak,
+                    "tensor_tops": 2 * v["macs"] / (v["ms"] * scale / 1e3) / 1e12} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    step_bytes = sum(g["bytes"] for g in agg.values())
     roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % which if which == "measured" else "fallback 6650 GB/s",
-            "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)" if traffic else None,
+            "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu, this build)" if traffic else None,
             "algorithmic_bytes_per_launch": t["bytes"] / t["launches"],
             "launches_per_step": t["launches"], "share_of_step": t["ms"] / total_ms,
-            "algorithmic_bytes_per_step": t["bytes"], "avg_launch_ms": t["ms"] / t["launches"],
-            "tensor_tops": 2 * t["macs"] / (t["ms"] / 1e3) / 1e12,
-            "note": "all %d %s launches of one step (the tcgen05 implicit-GEMM template behind hawq_conv2d and hawq_conv2d_dual): sum of algorithmic bytes / sum of CUDA-event durations (eager pass on the launch stream)" % (t["launches"], top)}
-    detail = {"layers": layers, "by_kernel": agg, "act_bytes": sum(g["bytes"] for g in agg.values()), "eager_step_ms": total_ms}
+            "algorithmic_bytes_per_step": t["bytes"], "avg_launch_ms": t["ms"] * scale / t["launches"],
+            "tensor_tops": 2 * t["macs"] / (t["ms"] * scale / 1e3) / 1e12,
+            "whole_step": {"algorithmic_bytes": step_bytes, "GBps": step_bytes / (graph_ms_per_step / 1e3) / 1e9,
+                           "frac_of_hbm_peak": step_bytes / (graph_ms_per_step / 1e3) / 1e9 / peak},
+            "families": families, "eager_event_sum_ms": total_ms, "graph_ms_per_step": graph_ms_per_step,
+            "note": "all %d %s launches of one step: sum of algorithmic bytes / (graph-timed ms per step of the timed region x the family's share of "
+                    "the per-launch CUDA-event times of an eager pass on the launch stream)" % (t["launches"], top)}
+    detail = {"layers": layers, "by_kernel": agg, "act_bytes": step_bytes, "eager_step_ms": total_ms, "graph_ms_per_step": graph_ms_per_step}
     return roof, detail
 
 

@@ -7,6 +7,7 @@
 
 #include <cstdlib>
 
+#include "conv_halo.h"
 #include "conv_igemm.cuh"
 #include "conv_tc.cuh"
 #include "elementwise.cuh"
@@ -21,7 +22,7 @@ struct hawq_handle {
 };
 
 static thread_local char g_err[512] = "";
-static long long* g_trace = nullptr;   // hawq_debug_set_trace
+static long long g_kernel_count[4] = {0, 0, 0, 0};   // hawq_debug_kernel_count: launches by kernel family (not atomic: debugging aid)
 
 // ---- TMA tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda)
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -102,31 +103,6 @@ static int set_tc_attr1() {
   CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64, EPI, WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, EPI, true>::TOTAL));
   return HAWQ_OK;
 }
-// 16-epilogue-warp variants (uint16-stream epilogues, 128-column tiles)
-template <int EPI>
-static int set_tc_attr_ew16() {
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, false, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI, false, 16>::TOTAL));
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, true, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI, false, 16>::TOTAL));
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, false, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI, true, 16>::TOTAL));
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, EPI, true, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, EPI, true, 16>::TOTAL));
-  return HAWQ_OK;
-}
-static int set_tc_attr_lean() {
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, TC_EPI_REQ, false, false, TC_EPI_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, TC_EPI_REQ, false>::TOTAL));
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64, TC_EPI_REQ, false, false, TC_EPI_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, TC_EPI_REQ, false>::TOTAL));
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<128, TC_EPI_REQ, false, true, TC_EPI_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128, TC_EPI_REQ, true>::TOTAL));
-  CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<64, TC_EPI_REQ, false, true, TC_EPI_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64, TC_EPI_REQ, true>::TOTAL));
-  return HAWQ_OK;
-}
-static bool mma_fast_enabled() {
-  static const bool on = [] { const char* e = getenv("HAWQ_B200_MMA_FAST"); return e && e[0] == '1'; }();   // opt-in until validated on hardware
-  return on;
-}
-static bool epi16_enabled() {
-  static const bool on = [] { const char* e = getenv("HAWQ_B200_EPI16"); return e && e[0] == '1'; }();   // opt-in until validated on hardware
-  return on;
-}
-
 template <int EPI>
 static int set_tc_attr() {
   int rc = set_tc_attr1<EPI, false>();
@@ -136,34 +112,24 @@ static int set_tc_attr() {
 
 // conv_tc launches carry the programmatic-stream-serialization attribute (HAWQ_B200_PDL != 0): the kernel's prologue may
 // start while the previous kernel of the stream drains; the kernel itself waits (griddepcontrol.wait) before touching memory
-template <int BN, int EPI, bool WIDE, bool A4, int EW = TC_EPI_WARPS, bool LEAN = false>
+template <int BN, int EPI, bool WIDE, bool A4>
 static void launch_tc3(const ConvParams& p, const TcMaps& maps, int grid, cudaStream_t st) {
   static const bool pdl = [] { const char* e = getenv("HAWQ_B200_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(tc_threads(EW), 1, 1);
-  cfg.dynamicSmemBytes = TcSmem<BN, EPI, A4, EW>::TOTAL;
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = TcSmem<BN, EPI, A4>::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, EPI, WIDE, A4, EW, LEAN>, p, maps);   // errors surface through launch_check()
+  cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, EPI, WIDE, A4>, p, maps);   // errors surface through launch_check()
 }
 template <int EPI, bool WIDE, bool A4>
 static void launch_tc2(const ConvParams& p, const TcMaps& maps, bool bn128, int grid, cudaStream_t st) {
-  if constexpr (EPI == TC_EPI_RES22 || EPI == TC_EPI_DUAL) {
-    if (bn128 && p.epi16) { launch_tc3<128, EPI, WIDE, A4, 16>(p, maps, grid, st); return; }
-  }
-  if constexpr (EPI == TC_EPI_REQ && !WIDE) {
-    if (p.mma_fast) {
-      if (bn128) launch_tc3<128, EPI, WIDE, A4, TC_EPI_WARPS, true>(p, maps, grid, st);
-      else launch_tc3<64, EPI, WIDE, A4, TC_EPI_WARPS, true>(p, maps, grid, st);
-      return;
-    }
-  }
   if (bn128) launch_tc3<128, EPI, WIDE, A4>(p, maps, grid, st);
   else launch_tc3<64, EPI, WIDE, A4>(p, maps, grid, st);
 }
@@ -207,11 +173,9 @@ int hawq_create(int device, hawq_handle** out) {
   CUDA_TRY(cudaMemset(h->status, 0, sizeof(int32_t)));
   int rc;
   if ((rc = set_tc_attr<TC_EPI_REQ>()) || (rc = set_tc_attr<TC_EPI_RAW>()) || (rc = set_tc_attr<TC_EPI_RES22>()) ||
-      (rc = set_tc_attr<TC_EPI_RES44>()) || (rc = set_tc_attr<TC_EPI_RES42>()) || (rc = set_tc_attr<TC_EPI_DUAL>()) ||
-      // opt-in variants: configured only when requested, so the default start-up sequence is exactly the validated one
-      (epi16_enabled() && ((rc = set_tc_attr_ew16<TC_EPI_RES22>()) || (rc = set_tc_attr_ew16<TC_EPI_DUAL>()))) ||
-      (mma_fast_enabled() && (rc = set_tc_attr_lean())))
+      (rc = set_tc_attr<TC_EPI_RES44>()) || (rc = set_tc_attr<TC_EPI_RES42>()) || (rc = set_tc_attr<TC_EPI_DUAL>()))
     return rc;
+  if ((rc = halo_set_attributes())) return fail(rc, "%s", halo_last_error());
   CUDA_TRY(cudaFuncSetAttribute(linear_dp4a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, linear_smem_bytes(LIN_MAX_K)));
   if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
       (rc = set_conv_attr<64, true>()))
@@ -289,13 +253,11 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   p.y_bits = ep->y_bits; p.low_bits = ep->low_bits; p.low_m = ep->low_m; p.low_e = ep->low_e;
   p.low_lo = ep->low_lo; p.low_hi = ep->low_hi; p.cout_store = ep->cout_store;
   p.slow_scalar = 0;
-  p.trace = g_trace;
   p.tma_a = 0;
   p.tma_io = 0;
   p.patch_rows = 0;
   p.w_tiled = nullptr;
   p.sat_pack = sat_pack_enabled() ? 1 : 0;
-  p.mma_fast = mma_fast_enabled() ? 1 : 0;
   if (ep->mode == HAWQ_EPI_RESIDUAL) {
     if (ep->res_kind == 0 && !dyadic_is_fast(ep->res_m, ep->res_e)) p.slow_scalar = 1;
     if (ep->low_bits != 0 && !dyadic_is_fast(ep->low_m, ep->low_e)) p.slow_scalar = 1;
@@ -348,6 +310,13 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   const bool folds = ep->mode != HAWQ_EPI_RESIDUAL || ((ep->res_kind != 0 || fold_ok(ep->res_m, ep->res_e)) && (ep->low_bits == 0 || fold_ok(ep->low_m, ep->low_e)));
   if (tc_enabled && tc_epi && folds && (ratios_one || ratios_wide)) {
     const bool a4 = d->a_bits == 4;
+    // 3x3 stride-1 REQUANT layers: A operand read in place from a zero-padded TMA patch, weights stationary (conv_halo.cuh)
+    if (d->w_layout == 1 && ep->mode == HAWQ_EPI_REQUANT) {
+      const int hr = launch_conv_halo(h->sm_count, d, ep, x, w + (size_t)d->Cout * p.K, chan, out, h->status, stream);
+      if (hr < 0) return fail(hr, "%s", halo_last_error());
+      if (hr == 0) { ++g_kernel_count[1]; return launch_check("conv_halo"); }
+    }
+    ++g_kernel_count[0];
     const int bn = (d->Cout % 128 == 0) ? 128 : 64;
     TcMaps maps;
     memset(&maps, 0, sizeof(maps));
@@ -371,8 +340,7 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
       p.patch_rows = (int)rows;
     }
     if (ep->mode == HAWQ_EPI_RESIDUAL && ep->res_kind == 0 && ep->res_bits == 16 && ep->y_bits == 16) {
-      p.epi16 = (epi16_enabled() && bn == 128) ? 1 : 0;
-      const uint32_t cw = p.epi16 ? bn / 4 : bn / 2;   // columns per epilogue warp
+      const uint32_t cw = bn / 2;   // columns per epilogue warp
       const CUtensorMapSwizzle sw_y = cw * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
       int bad = make_map_2d(&maps.res, res, (uint64_t)d->Cout * 2, (uint64_t)M, (uint64_t)d->Cout * 2, cw * 2, 32, sw_y);
       bad |= make_map_2d(&maps.y, out, (uint64_t)d->Cout * 2, (uint64_t)M, (uint64_t)d->Cout * 2, cw * 2, 32, sw_y);
@@ -448,19 +416,16 @@ int hawq_conv2d_dual(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogu
   p.Ho = d->H; p.Wo = d->W; p.M = (int)M; p.K = d->Cin; p.cin_chunks = d->Cin / 64; p.x_pix_bytes = d->Cin * d->a_bits / 8;
   p.mode = ep->mode; p.relu = 1; p.res_kind = 1; p.y_bits = 16; p.low_bits = ep->low_bits; p.low_m = ep->low_m; p.low_e = ep->low_e;
   p.low_lo = ep->low_lo; p.low_hi = ep->low_hi;
-  p.trace = g_trace;
   p.w_tiled = w + (size_t)d->Cout * d->Cin;
   p.dual = 1;
   p.sat_pack = sat_pack_enabled() ? 1 : 0;
-  p.mma_fast = mma_fast_enabled() ? 1 : 0;
   p.x2 = (const uint8_t*)x2; p.w2_tiled = w2 + (size_t)d2->Cout * d2->Cin; p.chan2 = chan2;
   p.H2 = d2->H; p.W2 = d2->W; p.stride2 = d2->stride; p.cin_chunks2 = d2->Cin / 64; p.x2_pix_bytes = d2->Cin * d2->a_bits / 8;
   p.tma_io = 1;
 
   const bool a4 = d->a_bits == 4;
   const bool bn128 = (d->Cout % 128 == 0);
-  p.epi16 = (epi16_enabled() && bn128) ? 1 : 0;
-  const uint32_t cw = p.epi16 ? 32 : (bn128 ? 128 : 64) / 2;
+  const uint32_t cw = (bn128 ? 128 : 64) / 2;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   const CUtensorMapSwizzle sw_y = cw * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -519,13 +484,10 @@ int hawq_stem_conv_i8(hawq_handle* h, int32_t N, int32_t H, int32_t W, const int
   if (N > 65535) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_stem_conv_i8: N > 65535");
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   const dim3 grid((Wo + STEM_TW - 1) / STEM_TW, (Ho + STEM_TH - 1) / STEM_TH, N);
-  static const bool persist = [] { const char* e = getenv("HAWQ_B200_STEM_PERSIST"); return e && e[0] == '1'; }();   // opt-in until validated
-  if (persist) {
-    const long long tiles = (long long)N * grid.x * grid.y;
-    const int ctas = (int)(tiles < 4LL * h->sm_count ? tiles : 4LL * h->sm_count);
-    stem_conv_kernel<true><<<ctas, 256, 0, (cudaStream_t)stream>>>(x, (const uint32_t*)w, chan, N, H, W, Ho, Wo, clamp_lo, clamp_hi, out);
-  } else
-  stem_conv_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const uint32_t*)w, chan, N, H, W, Ho, Wo, clamp_lo, clamp_hi, out);
+  // persistent: 4 CTAs per SM loop over the tiles and stage the weights once (round-2 A/B: 0.212 -> 0.202 ms at batch 128)
+  const long long tiles = (long long)N * grid.x * grid.y;
+  const int ctas = (int)(tiles < 4LL * h->sm_count ? tiles : 4LL * h->sm_count);
+  stem_conv_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(x, (const uint32_t*)w, chan, N, H, W, Ho, Wo, clamp_lo, clamp_hi, out);
   return launch_check("stem_conv");
 }
 
@@ -675,9 +637,6 @@ int hawq_retile_weights(hawq_handle* h, const int8_t* w_ohwi, int32_t Cout, int6
   return launch_check("retile_weights");
 }
 
-int hawq_debug_set_trace(int64_t* device_buffer) {
-  g_trace = reinterpret_cast<long long*>(device_buffer);
-  return HAWQ_OK;
-}
+int64_t hawq_debug_kernel_count(int32_t family) { return (family >= 0 && family < 4) ? g_kernel_count[family] : -1; }
 
 }  // extern "C"

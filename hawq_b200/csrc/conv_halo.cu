@@ -1,0 +1,142 @@
+// Host side of the in-place 3x3 convolution (conv_halo.cuh): applicability, shared-memory plan, 4-D tensor map, launch.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "conv_halo.cuh"
+#include "conv_halo.h"
+
+namespace hawq {
+
+static thread_local char g_halo_err[256] = "";
+const char* halo_last_error() { return g_halo_err; }
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return reinterpret_cast<encode_tiled_fn>(ptr);
+  }();
+  return fn;
+}
+
+constexpr int HALO_SMEM_MAX = 232448;   // 227 KB
+
+struct HaloPlan {
+  int bn, npb, nkb, total;
+  HaloParams p;
+};
+
+static int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// shared-memory carve-up for channel-block width bn; returns false if it does not fit
+static bool plan_for(int bn, bool a4, int K, int wp, int R, HaloPlan* out) {
+  const int b_bytes = (K / 64) * bn * 64;
+  const int patch_alloc = round_up((128 + 2 * wp + 2) * 64, 1024);
+  const int packed_alloc = a4 ? round_up((R + 2) * wp * 32, 1024) : 0;
+  const int stage = 8 * 32 * (bn / 2 + 16);
+  const int cst = bn * 16;
+  const int bars = 256;
+  for (int npb = a4 ? 2 : HALO_MAX_BUFS; npb >= 2; --npb) {
+    const int nkb = a4 ? 3 : 0;
+    int off = round_up(b_bytes, 1024);
+    HaloParams& p = out->p;
+    p.off_patch = off; off += npb * patch_alloc;
+    p.off_packed = off; off += nkb * packed_alloc;
+    p.off_stage = off; off += stage;
+    p.off_cst = off; off += cst;
+    p.off_bar = off; off += bars;
+    const int total = off + 1024;      // slack for the 1024-byte alignment of the base
+    if (total <= HALO_SMEM_MAX) {
+      out->bn = bn; out->npb = npb; out->nkb = nkb; out->total = total;
+      p.patch_alloc = patch_alloc; p.packed_alloc = packed_alloc; p.npb = npb; p.nkb = nkb;
+      return true;
+    }
+  }
+  return false;
+}
+
+int halo_set_attributes() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(conv_halo_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_halo_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_halo_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_halo_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess) {
+    snprintf(g_halo_err, sizeof(g_halo_err), "conv_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return HAWQ_ERR_CUDA;
+  }
+  return HAWQ_OK;
+}
+
+template <int BN, bool A4>
+static void launch(const HaloPlan& plan, const CUtensorMap& map, int grid, cudaStream_t st) {
+  static const bool pdl = [] { const char* e = getenv("HAWQ_B200_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(HALO_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)plan.total;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, A4>, plan.p, map);
+}
+
+int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x, const int8_t* w_tiled,
+                     const hawq_chan* chan, void* out, int32_t* status, void* stream) {
+  static const int mode = [] { const char* e = getenv("HAWQ_B200_HALO"); return e ? atoi(e) : 1; }();   // 0: off; 2: with the descriptor base-offset field
+  if (!mode) return 1;
+  if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1 || d->w_layout != 1) return 1;
+  if (ep->mode != HAWQ_EPI_REQUANT || (ep->out_bits != 8 && ep->out_bits != 4) || !(ep->flags & HAWQ_EP_RATIOS_LE_ONE)) return 1;
+  const int wp = d->W + 2;
+  if (wp > 128 || wp > 256) return 1;
+  const bool a4 = d->a_bits == 4;
+  const int R = d->H < 128 / wp ? d->H : 128 / wp;
+  const int K = 9 * d->Cin;
+  HaloPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  if (!((d->Cout % 128 == 0 && plan_for(128, a4, K, wp, R, &plan)) || plan_for(64, a4, K, wp, R, &plan))) return 1;
+  HaloParams& p = plan.p;
+  p.w_tiled = w_tiled; p.tiled_bn = (d->Cout % 128 == 0) ? 128 : 64;
+  p.chan = chan; p.out = (uint8_t*)out; p.status = status;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cout = d->Cout; p.chunks = d->Cin / 64; p.R = R; p.wp = wp;
+  p.tiles_per_img = (d->H + R - 1) / R;
+  const long long m_tiles = (long long)d->N * p.tiles_per_img;
+  if (m_tiles > 0x7fffffff) return 1;
+  p.m_tiles = (int)m_tiles; p.n_tiles = d->Cout / plan.bn;
+  int per_n = sm_count / p.n_tiles;
+  if (per_n < 1) return 1;
+  if (per_n > p.m_tiles) per_n = p.m_tiles;
+  p.ctas_per_n = per_n;
+  p.patch_bytes = (R + 2) * wp * (a4 ? 32 : 64);
+  p.relu = ep->relu; p.out_bits = ep->out_bits; p.lo = ep->clamp_lo; p.hi = ep->clamp_hi;
+  p.desc_bo = mode == 2 ? 1 : 0;
+
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) { snprintf(g_halo_err, sizeof(g_halo_err), "conv_halo: cuTensorMapEncodeTiled unavailable"); return HAWQ_ERR_CUDA; }
+  CUtensorMap map;
+  const uint64_t cb = (uint64_t)d->Cin * d->a_bits / 8;       // bytes per pixel
+  const cuuint64_t dims[4] = {cb, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+  const cuuint64_t strides[3] = {cb, cb * d->W, cb * d->W * d->H};
+  const cuuint32_t box[4] = {a4 ? 32u : 64u, (cuuint32_t)wp, (cuuint32_t)(R + 2), 1u};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         a4 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(g_halo_err, sizeof(g_halo_err), "conv_halo: cuTensorMapEncodeTiled failed (%d)", (int)r); return HAWQ_ERR_CUDA; }
+
+  const int grid = p.n_tiles * p.ctas_per_n;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan.bn == 128) { if (a4) launch<128, true>(plan, map, grid, st); else launch<128, false>(plan, map, grid, st); }
+  else { if (a4) launch<64, true>(plan, map, grid, st); else launch<64, false>(plan, map, grid, st); }
+  return 0;
+}
+
+}  // namespace hawq

@@ -1,0 +1,298 @@
+// 3x3 stride-1 pad-1 convolution with the A operand read IN PLACE from a zero-padded input patch, weights stationary.
+//
+// Output positions are enumerated in the PADDED coordinate system of one image: a tile covers R output rows y0 .. y0 + R - 1
+// and all W + 2 padded columns, position p = (y - y0) * (W + 2) + x, p < R * (W + 2) <= 128; columns x >= W are waste
+// (2 / (W + 2) of the MMA rows).  One 4-D TMA box {64 channels, W + 2, R + 2, 1 image} at (c0, -1, y0 - 1, n) lands the
+// input rows y0 - 1 .. y0 + R with the left / right / top / bottom padding zero-filled by the TMA unit, as a matrix of
+// (R + 2) * (W + 2) rows x 64 B in the UMMA K-major SWIZZLE_64B layout.  In that matrix the im2col row of position p for
+// tap (kh, kw) is row p + kh * (W + 2) + kw: a constant row shift.  So tcgen05.mma reads its A operand straight from the
+// patch with the descriptor start address advanced by (kh * (W + 2) + kw) * 64 bytes (the swizzle is a function of the
+// shared-memory address bits, tools/probe_b200.cu part A) - no im2col copy, no producer warps, no per-k-tile barriers:
+// per (tile, 64-channel chunk) one TMA load, one barrier wait, 18 MMAs (9 taps x K = 2 x 32), one commit.
+// L2 -> SM traffic is ~ (R + 2) / R of the input instead of 9x.
+//
+// The weights of the CTA's channel block ([9 * Cin / 64] pre-swizzled BN x 64 B blocks, hawq_retile_weights) are loaded
+// once and stay in shared memory; a CTA keeps its channel block and walks over image row groups.
+//
+//   warp  0     one elected lane: weight load, patch TMA loads (A4: all of warps 0-3 expand packed 4-bit patches to int8,
+//               once per patch instead of once per tap)
+//   warp  4     one elected lane issues tcgen05.mma kind::i8 into one of two TMEM accumulators
+//   warps 5-12  epilogue: tcgen05.ld, exact FP64-FMA dyadic requantisation (+bias, ReLU, clamp) -> int8 / packed uint4,
+//               staged per warp and written out row by row (rows of waste columns are skipped)
+// Semantics: QuantBnConv2d / QuantConv2d + QuantAct case 0, reference quant_modules.py:440-494, quant_utils.py:390-413.
+#pragma once
+#include "tc_ptx.cuh"
+
+namespace hawq {
+
+struct HaloParams {
+  const int8_t* w_tiled;     // [Cout / tiled_bn][9 * chunks][tiled_bn][64] pre-swizzled blocks (hawq_retile_weights)
+  int tiled_bn;              // rows per block of that copy (128 or 64); BN divides it
+  const hawq_chan* chan;
+  uint8_t* out;              // NHWC, out_bits 8 (int8) or 4 (packed, hawq nibble order)
+  int32_t* status;
+  int N, H, W, Cout;
+  int chunks;                // Cin / 64
+  int R;                     // output rows per tile
+  int wp;                    // W + 2
+  int tiles_per_img;         // ceil(H / R)
+  int m_tiles, n_tiles, ctas_per_n;
+  int patch_bytes;           // bytes of one TMA box: (R + 2) * (W + 2) * (A4 ? 32 : 64)
+  int patch_alloc;           // bytes per int8 patch buffer (>= (128 + 2 * wp + 2) * 64, multiple of 1024)
+  int packed_alloc;          // A4: bytes per packed patch buffer (multiple of 1024)
+  int npb, nkb;              // int8 patch buffers, packed patch buffers (A4)
+  int relu, out_bits, lo, hi;
+  int off_patch, off_packed, off_stage, off_cst, off_bar;   // shared-memory carve-up (bytes from the 1024-aligned base; weights at 0)
+  int desc_bo;               // 1: set the descriptor base-offset field from the start address
+};
+
+constexpr int HALO_THREADS = 13 * 32;   // 4 producer / converter warps, 1 MMA warp, 8 epilogue warps
+constexpr int HALO_MAX_BUFS = 4;
+
+// TMA: 4-D tiled box global -> shared
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+
+template <int BN, bool A4>
+__global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap xmap) {
+  constexpr int B_STAGE = BN * 64;
+  constexpr int CW = BN / 2;               // columns per epilogue warp
+  constexpr int STG_PITCH = CW + 16;       // staging row pitch (bytes): 16-byte row-per-lane accesses conflict-free
+  constexpr int TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t smem_base = smem_u32(smem);
+  double2* sCst = reinterpret_cast<double2*>(smem + p.off_cst);
+  const uint32_t bar_base = smem_base + p.off_bar;
+  const uint32_t b_full = bar_base;
+  auto pfull = [&](int b) { return bar_base + 8u * (1 + b); };
+  auto pempty = [&](int b) { return bar_base + 8u * (1 + HALO_MAX_BUFS + b); };
+  auto kfull = [&](int b) { return bar_base + 8u * (1 + 2 * HALO_MAX_BUFS + b); };
+  auto kempty = [&](int b) { return bar_base + 8u * (1 + 3 * HALO_MAX_BUFS + b); };
+  auto tfull = [&](int b) { return bar_base + 8u * (1 + 4 * HALO_MAX_BUFS + b); };
+  auto tempty = [&](int b) { return bar_base + 8u * (3 + 4 * HALO_MAX_BUFS + b); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_bar + 8 * (5 + 4 * HALO_MAX_BUFS));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nt = blockIdx.x % p.n_tiles, slot = blockIdx.x / p.n_tiles;
+  const int n0 = nt * BN;
+  const int KT = 9 * p.chunks;
+
+  if (tid == 0) {
+    mbar_init(b_full, 1);
+    for (int b = 0; b < HALO_MAX_BUFS; ++b) {
+      mbar_init(pfull(b), A4 ? 128 : 1);
+      mbar_init(pempty(b), 1);
+      mbar_init(kfull(b), 1);
+      mbar_init(kempty(b), 128);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull(b), 1);
+      mbar_init(tempty(b), 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  asm volatile("griddepcontrol.launch_dependents;");
+
+  if (warp < 4) {
+    // =============================================================================== producer (+ A4 converters)
+    // weights and per-channel constants are plan-time data: fetched before waiting for the previous kernel of the stream
+    if (warp == 0 && elect_one()) {
+      // rows n0 .. n0 + BN - 1 of k-tile kt: a contiguous (already swizzled: the pattern has period 8 rows) slice of its block
+      const int8_t* src = p.w_tiled + (size_t)(n0 / p.tiled_bn) * KT * (p.tiled_bn * 64) + (size_t)(n0 % p.tiled_bn) * 64;
+      mbar_arrive_expect_tx(b_full, (uint32_t)KT * B_STAGE);
+      for (int kt = 0; kt < KT; ++kt) bulk_load_1d(smem_base + (uint32_t)kt * B_STAGE, src + (size_t)kt * (p.tiled_bn * 64), B_STAGE, b_full);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if constexpr (!A4) {
+      if (warp == 0 && elect_one()) {
+        uint32_t b = 0, ph = 0;
+        for (int mt = slot; mt < p.m_tiles; mt += p.ctas_per_n) {
+          const int n_img = mt / p.tiles_per_img, y0 = (mt - n_img * p.tiles_per_img) * p.R;
+          for (int c = 0; c < p.chunks; ++c) {
+            mbar_wait_small(pempty(b), ph ^ 1);
+            mbar_arrive_expect_tx(pfull(b), (uint32_t)p.patch_bytes);
+            tma_load_4d(smem_base + p.off_patch + b * p.patch_alloc, &xmap, c * 64, -1, y0 - 1, n_img, pfull(b));
+            if (++b == (uint32_t)p.npb) { b = 0; ph ^= 1; }
+          }
+        }
+      }
+    } else {
+      // packed 4-bit patches: TMA -> packed buffer (rows of 32 B, SWIZZLE_32B) -> expanded by these 128 threads into the int8
+      // patch (rows of 64 B, SWIZZLE_64B) in the K order the permuted weights expect (per 32-channel block: low nibbles, high nibbles)
+      const int my_tiles = (slot < p.m_tiles) ? (p.m_tiles - 1 - slot) / p.ctas_per_n + 1 : 0;
+      const int total_g = my_tiles * p.chunks;
+      const int rows = p.patch_bytes / 32;
+      auto issue = [&](int g) {            // one elected lane of warp 0
+        const int t = g / p.chunks, c = g - t * p.chunks;
+        const int mt = slot + t * p.ctas_per_n;
+        const int n_img = mt / p.tiles_per_img, y0 = (mt - n_img * p.tiles_per_img) * p.R;
+        const int kb = g % p.nkb;
+        mbar_wait_small(kempty(kb), ((g / p.nkb) & 1) ^ 1);
+        mbar_arrive_expect_tx(kfull(kb), (uint32_t)p.patch_bytes);
+        tma_load_4d(smem_base + p.off_packed + kb * p.packed_alloc, &xmap, c * 32, -1, y0 - 1, n_img, kfull(kb));
+      };
+      if (warp == 0) {
+        for (int g = 0; g < p.nkb - 1 && g < total_g; ++g)
+          if (elect_one()) issue(g);
+        __syncwarp();
+      }
+      for (int g = 0; g < total_g; ++g) {
+        if (warp == 0) {
+          if (g + p.nkb - 1 < total_g && elect_one()) issue(g + p.nkb - 1);
+          __syncwarp();
+        }
+        const int kb = g % p.nkb, b = g % p.npb;
+        mbar_wait_small(kfull(kb), (g / p.nkb) & 1);
+        mbar_wait_small(pempty(b), ((g / p.npb) & 1) ^ 1);
+        const uint8_t* src = smem + p.off_packed + kb * p.packed_alloc;
+        uint8_t* dst = smem + p.off_patch + b * p.patch_alloc;
+        for (int r = tid; r < rows; r += 128) {
+          const uint32_t p_sw = (r >> 2) & 1, a_sw = (r >> 1) & 3;
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            const uint4 wv = *reinterpret_cast<const uint4*>(src + r * 32 + ((blk ^ p_sw) << 4));
+            const uint4 lo = make_uint4(wv.x & 0x0F0F0F0Fu, wv.y & 0x0F0F0F0Fu, wv.z & 0x0F0F0F0Fu, wv.w & 0x0F0F0F0Fu);
+            const uint4 hi = make_uint4((wv.x >> 4) & 0x0F0F0F0Fu, (wv.y >> 4) & 0x0F0F0F0Fu, (wv.z >> 4) & 0x0F0F0F0Fu, (wv.w >> 4) & 0x0F0F0F0Fu);
+            *reinterpret_cast<uint4*>(dst + r * 64 + (((2 * blk) ^ a_sw) << 4)) = lo;
+            *reinterpret_cast<uint4*>(dst + r * 64 + (((2 * blk + 1) ^ a_sw) << 4)) = hi;
+          }
+        }
+        fence_proxy_async();             // generic-proxy writes -> tcgen05.mma (async proxy) reads
+        mbar_arrive(pfull(b));
+        mbar_arrive(kempty(kb));
+      }
+    }
+  } else if (warp == 4) {
+    // =============================================================================== MMA issuer
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_i8(128, BN, !A4);     // packed 4-bit activations are unsigned
+      const uint64_t desc_hi = umma_desc_sw64(0) & 0xFFFFFFFF00000000ull;
+      auto desc = [&](uint32_t addr) {
+        uint64_t d = desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16));
+        if (p.desc_bo) d |= (uint64_t)((addr >> 7) & 7u) << 49;
+        return d;
+      };
+      mbar_wait_small(b_full, 0);
+      uint32_t b = 0, ph = 0, tile_iter = 0;
+      for (int mt = slot; mt < p.m_tiles; mt += p.ctas_per_n, ++tile_iter) {
+        const uint32_t buf = tile_iter & 1;
+        mbar_wait_small(tempty(buf), ((tile_iter >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int c = 0; c < p.chunks; ++c) {
+          mbar_wait_small(pfull(b), ph);
+          tc_fence_after();
+          const uint32_t patch = smem_base + p.off_patch + b * p.patch_alloc;
+          uint32_t wblk = smem_base + (uint32_t)c * B_STAGE;         // k-tile index = tap * chunks + c
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t a_addr = patch + (uint32_t)(kh * p.wp + kw) * 64u;
+              const uint64_t bd = desc_hi | (uint64_t)((wblk >> 4) | (1u << 16));
+              umma_i8(d_tmem, desc(a_addr), bd, idesc, (c | kh | kw) != 0 ? 1u : 0u);
+              umma_i8(d_tmem, desc(a_addr + 32), bd + 2, idesc, 1u);
+              wblk += (uint32_t)p.chunks * B_STAGE;
+            }
+          }
+          umma_commit(pempty(b));
+          if (++b == (uint32_t)p.npb) { b = 0; ph ^= 1; }
+        }
+        umma_commit(tfull(buf));
+      }
+    }
+  } else {
+    // =============================================================================== epilogue (8 warps)
+    const int ew = warp - 5;
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                    // column half
+    uint8_t* stage = smem + p.off_stage + ew * (32 * STG_PITCH);
+    uint8_t* mystage = stage + lane * STG_PITCH;
+    constexpr double kMagic = 6755399441055744.0, kOffS = 4503601774854144.0;
+    const int q_lo = p.relu ? max(p.lo, 0) : p.lo, q_hi = p.hi;
+    int bad = 0;
+    // per-channel constants of this CTA's channel block (plan-time data)
+    for (int i = tid - 5 * 32; i < BN; i += 8 * 32) {
+      const hawq_chan ch = p.chan[n0 + i];
+      sCst[i] = make_double2(kOffS - (double)ch.bias, dyadic_to_double(ch.m, ch.e));
+      bad |= !(ch.m == 0u || ch.e >= 31) | (ch.bias >= (1 << 29)) | (ch.bias <= -(1 << 29));
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(8 * 32));
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int c0 = n0 + half * CW;
+    const int used = p.R * p.wp;                 // positions of a tile
+    uint32_t tile_iter = 0;
+    for (int mt = slot; mt < p.m_tiles; mt += p.ctas_per_n, ++tile_iter) {
+      const int n_img = mt / p.tiles_per_img, y0 = (mt - n_img * p.tiles_per_img) * p.R;
+      const uint32_t buf = tile_iter & 1;
+      mbar_wait_small(tfull(buf), (tile_iter >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < CW; cb += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + half * CW + cb, acc);
+        tmem_ld_wait();
+        const double2* cst = sCst + half * CW + cb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 16) {
+          int q[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const double2 cm = cst[j + k];
+            const double d = __hiloint2double(0x43300000, acc[j + k] ^ 0x80000000) - cm.x;
+            q[k] = clampi(__double2loint(__fma_rn(d, cm.y, kMagic)), q_lo, q_hi);
+          }
+          auto pack4 = [](int a, int b, int c, int d) { return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410); };
+          if (p.out_bits == 8) {
+            *reinterpret_cast<uint4*>(mystage + cb + j) =
+                make_uint4(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7]), pack4(q[8], q[9], q[10], q[11]), pack4(q[12], q[13], q[14], q[15]));
+          } else {
+            *reinterpret_cast<uint2*>(mystage + ((cb + j) >> 1)) =
+                make_uint2(pack_nibbles8(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7])),
+                           pack_nibbles8(pack4(q[8], q[9], q[10], q[11]), pack4(q[12], q[13], q[14], q[15])));
+          }
+        }
+      }
+      // accumulator buffer fully read: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(buf));
+      // copy-out: a warp instruction writes whole rows; rows of waste columns / past the image are skipped
+      const int row_bytes = CW * p.out_bits / 8;       // 64 / 32 (8-bit), 32 / 16 (4-bit)
+      const int cpr = row_bytes / 16;                  // 16-byte chunks per row: 4 / 2 / 1
+      const size_t img_base = (size_t)n_img * p.H * p.W;
+      for (int id = lane; id < 32 * cpr; id += 32) {
+        const int rr = id / cpr, j = id - rr * cpr;
+        const int pos = quarter * 32 + rr;
+        const int y = pos / p.wp, x = pos - y * p.wp;
+        if (pos < used && x < p.W && y0 + y < p.H) {
+          const int4 v = *reinterpret_cast<const int4*>(stage + rr * STG_PITCH + j * 16);
+          uint8_t* g = p.out + (((img_base + (size_t)(y0 + y) * p.W + x) * p.Cout + c0) * p.out_bits >> 3) + j * 16;
+          *reinterpret_cast<int4*>(g) = v;
+        }
+      }
+      __syncwarp();   // the staging slice is rewritten by the next tile
+    }
+    if (bad) atomicOr(p.status, HAWQ_FLAG_BAD_RATIO);
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace hawq

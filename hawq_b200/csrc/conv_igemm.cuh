@@ -52,9 +52,6 @@ struct ConvParams {
   const int8_t* w2_tiled; // its re-tiled weights
   const hawq_chan* chan2; // its bias and the case-1 identity ratio (m1, e1) per channel
   int H2, W2, stride2, cin_chunks2, x2_pix_bytes;
-  long long* trace;  // debug timeline (hawq_debug_set_trace): [role][tile][event] clock64 values of CTA 0, or null
-  int mma_fast;           // tcgen05 kernels: lean MMA issue loop (opt-in, HAWQ_B200_MMA_FAST=1)
-  int epi16;              // host-side launch choice: 16-epilogue-warp variant of the uint16-stream kernels (maps built for BN / 4 columns)
 };
 
 constexpr int CONV_BM = 128;

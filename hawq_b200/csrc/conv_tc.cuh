@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "conv_igemm.cuh"
+#include "tc_ptx.cuh"
 
 namespace hawq {
 
@@ -42,12 +43,9 @@ struct alignas(64) TcMaps {
 
 constexpr int TC_BM = 128;
 constexpr int TC_PRODUCER_WARPS = 4;
-constexpr int TC_EPI_WARPS = 8;          // default epilogue width; the EW = 16 variants (RES22 / DUAL, BN = 128) use 16 warps
+constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_MMA_WARP = TC_PRODUCER_WARPS;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1 + TC_EPI_WARPS) * 32;   // 416
-// EW = 16: warps 0-3 producers, 4 MMA, 5-7 idle (register donors: setmaxnreg works on aligned groups of 4 warps), 8-23 epilogue
-__host__ __device__ constexpr int tc_epi_warp0(int ew) { return ew == 16 ? 8 : TC_MMA_WARP + 1; }
-__host__ __device__ constexpr int tc_threads(int ew) { return ew == 16 ? 24 * 32 : TC_THREADS; }
 
 // epilogue variants (compile-time): element sizes of the residual operand read into / the output staged in the slice
 constexpr int TC_EPI_REQ = 0;      // REQUANT -> 4/8 bit
@@ -57,9 +55,9 @@ constexpr int TC_EPI_RES44 = 3;    // RESIDUAL: int32 in (stream or identity-con
 constexpr int TC_EPI_RES42 = 4;    // RESIDUAL: int32 in, uint16 out
 constexpr int TC_EPI_DUAL = 5;     // RESIDUAL whose identity operand is a second in-kernel 1x1 convolution (two TMEM accumulators), uint16 out
 
-template <int BN, int EPI, bool A4 = false, int EW = TC_EPI_WARPS>
+template <int BN, int EPI, bool A4 = false>
 struct TcSmem {
-  static_assert(EW == 8 || (EW == 16 && BN == 128), "16 epilogue warps: 128-column tiles only");
+  static constexpr int EW = TC_EPI_WARPS;
   // pipeline depth: RESIDUAL epilogues are epilogue-bound and need shared memory for their tiles; the others are
   // load-latency-bound and get a deep ring.  The producer keeps LAG + 1 k-tiles in flight per thread.
   static constexpr int STAGES = (EPI == TC_EPI_RES22) ? (A4 && BN == 128 ? 4 : 5) : (EPI == TC_EPI_DUAL) ? 6 : (EPI >= TC_EPI_RES44) ? 5 : (EPI == TC_EPI_RAW) ? 7 : (BN == 128 ? 8 : 10);
@@ -74,10 +72,10 @@ struct TcSmem {
   static constexpr int SLICE_ES = RES_ES > Y_ES ? RES_ES : Y_ES;
   static constexpr bool TMA_IO = (EPI == TC_EPI_RES22 || EPI == TC_EPI_DUAL);                    // residual tile in / outputs out as swizzled TMA boxes
   static constexpr int SLICE_PITCH = TMA_IO ? CW * SLICE_ES : CW * SLICE_ES + 16;   // padded: 16-byte row-per-lane accesses conflict-free
-  static constexpr int SLICE = SLICE_ES ? (TMA_IO ? (EW == 8 ? 4096 : 32 * CW * 2) : 32 * SLICE_PITCH) : 0;
+  static constexpr int SLICE = SLICE_ES ? (TMA_IO ? 4096 : 32 * SLICE_PITCH) : 0;
   static constexpr int SLICE_BUFS = (EPI == TC_EPI_RES22) ? 3 : 1;         // RES22: 2 prefetch + 1 output; RES4x: in place; RAW: output
   static constexpr int LOW_PITCH = TMA_IO ? CW : CW + 16;
-  static constexpr int LOW_SLICE = (EPI == TC_EPI_RAW) ? 0 : (TMA_IO ? (EW == 8 ? 2048 : 32 * CW) : 32 * LOW_PITCH);   // TMA boxes keep 1024 B alignment
+  static constexpr int LOW_SLICE = (EPI == TC_EPI_RAW) ? 0 : (TMA_IO ? 2048 : 32 * LOW_PITCH);   // TMA boxes keep 1024 B alignment
   static constexpr int SLICES_OFF = RING;
   static constexpr int LOW_OFF = SLICES_OFF + EW * SLICE * SLICE_BUFS;
   static constexpr int CST_OFF = LOW_OFF + EW * LOW_SLICE;       // double2 {Cb, M}[BN]
@@ -91,142 +89,6 @@ struct TcSmem {
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-// ---------------------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a broken pipeline protocol becomes a trap (cudaErrorLaunchFailure), never a hung GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t i = 0; i < 4000000u; ++i)
-    if (mbar_try_wait(bar, parity)) return;
-  __trap();
-}
-// same, but the spin loop is not unrolled: ~8 instead of ~270 SASS instructions per call site (the unrolled form makes the kernels
-// 2x larger and shows up as instruction-fetch stalls); used by the LEAN variant
-__device__ __forceinline__ void mbar_wait_small(uint32_t bar, uint32_t parity) {
-#pragma unroll 1
-  for (uint32_t i = 0; i < 4000000u; ++i)
-    if (mbar_try_wait(bar, parity)) return;
-  __trap();
-}
-// the mbarrier arrives (count not incremented) once all cp.async operations previously issued by this thread have landed
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// TMA: 2-D tiled box global -> shared, completion (bytes) on an mbarrier
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-// 1-D bulk copy global -> shared (contiguous bytes, multiple of 16), completion (bytes) on an mbarrier
-__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
-}
-// TMA: 2-D tiled box shared -> global (bulk async group)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t smem_src) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_src) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// one lane of a converged warp
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
-      "selp.u32 %0, 1, 0, px;\n\t}"
-      : "=r"(pred));
-  return pred;
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], int8 x int8 -> int32
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      :
-      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives row (lane quarter base + i)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// bulk-copy (TMA) store groups
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// dense row-major tile written / read by TMA with the swizzle mode matching its row length (128/64/32/16 B rows ->
-// SWIZZLE_128B/64B/32B/NONE): byte offset of 16-byte chunk j of row l
-__device__ __forceinline__ uint32_t tma_tile_off(int row_bytes, int l, int j) {
-  const int x = row_bytes == 128 ? (l & 7) : row_bytes == 64 ? ((l >> 1) & 3) : row_bytes == 32 ? ((l >> 2) & 1) : 0;
-  return (uint32_t)(l * row_bytes + ((j ^ x) << 4));
-}
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row atoms of 512 B (SBO), version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)4 << 61);
-}
-// instruction descriptor: D = S32, A/B = signed int8, K-major both, N, M
-__host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n, bool a_signed) {
-  return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
 // ---------------------------------------------------------------------------------------------- kernel
 // WIDE: dyadic ratios up to 2^20 are allowed (e >= 11).  The FMA result is then checked to be a valid int32
 // (high word + sign bit of the low word must equal the high word of 1.5 * 2^52); a violation raises
@@ -236,15 +98,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n, bool a_signed
 // K order the (host-permuted) weights expect: per 32-channel block {c0-3, c8-11, c16-19, c24-27 | c4-7, c12-15, ...}.
 // Preconditions (promised via HAWQ_EP_RATIOS_*, re-checked -> HAWQ_FLAG_BAD_RATIO): ratios within the bound,
 // |bias| < 2^29 (sums of two requantised terms then cannot wrap), RESIDUAL launches have relu = 1.
-// EW: epilogue warps.  8 (default) or 16: the uint16-stream epilogues are instruction-latency bound with two epilogue warps
-// per SM sub-partition (profiles/r01/d1_ncu_full_conv_tc.txt: 45 % issue utilisation, "wait" stalls dominate); with 16 warps
-// each TMEM lane quarter is served by four warps of BN / 4 columns and registers are moved from the producer / MMA warp
-// groups to the epilogue groups with setmaxnreg.  Opt-in (HAWQ_B200_EPI16=1) until validated on hardware.
-// LEAN: lean MMA issue loop (REQUANT kernels, opt-in HAWQ_B200_MMA_FAST=1), see the comment at the loop.
-template <int BN, int EPI, bool WIDE, bool A4, int EW = TC_EPI_WARPS, bool LEAN = false>
-__global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvParams p, const __grid_constant__ TcMaps maps) {
-  using S = TcSmem<BN, EPI, A4, EW>;
-  constexpr int EPI_WARP0 = tc_epi_warp0(EW);    // first epilogue warp
+// Single-lane roles (TMA / bulk-copy issue, MMA issue) pick their lane with elect.sync from the converged warp: nvcc then emits
+// straight-line UTMALDG / UBLKCP / UTCIMMA / UTCBAR, whereas issue from a `lane == 0` branch is wrapped in an ELECT + BRA.U.ANY
+// loop per instruction.  Barrier waits use a non-unrolled bounded spin loop (~8 SASS instructions per call site).  (Round-2
+// A/B on B200, ResNet-50 W8A8 batch 128: 2.539 -> 2.433 ms/step, profiles/r02/a0_variants.txt.)
+template <int BN, int EPI, bool WIDE, bool A4>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvParams p, const __grid_constant__ TcMaps maps) {
+  using S = TcSmem<BN, EPI, A4>;
+  constexpr int EW = TC_EPI_WARPS;
+  constexpr int EPI_WARP0 = TC_MMA_WARP + 1;     // first epilogue warp
   constexpr int BM = TC_BM, STAGES = S::STAGES, LAG = S::LAG;
   constexpr int CW = S::CW;                      // columns handled by one epilogue warp: 32 or 64
   constexpr int TMEM_COLS = (EPI == TC_EPI_DUAL ? 4 : 2) * BN;   // two accumulator buffers (x2 accumulators in dual mode): 128 / 256 / 512
@@ -269,22 +131,9 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
   auto patch_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + 2 * EW + b); };            // TMA input patches (3x3 patch mode)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // debug timeline: role 0 producer (warp 0), 1 MMA, 2 epilogue (first epilogue warp); 8 events x 64 tiles per role
-  auto trace = [&](int role, uint32_t tile_i, int ev) {
-    if constexpr (!LEAN) {     // the lean variant carries no tracing code at all
-      if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tile_i < 64) p.trace[(role * 64 + tile_i) * 8 + ev] = clock64();
-    }
-  };
-  auto kwait = [&](uint32_t bar, uint32_t parity) {
-    if constexpr (LEAN || EW == 16) mbar_wait_small(bar, parity);     // the opt-in variants
-    else mbar_wait(bar, parity);
-  };
-  // the thread that issues TMA / bulk copies on behalf of the producers: thread 0, or (LEAN) a lane of warp 0 picked with elect.sync so
-  // that nvcc emits the issue straight-line (see the MMA issuer)
-  auto tma_issuer = [&]() -> bool {
-    if constexpr (LEAN) return warp == 0 && elect_one() != 0;
-    else return tid == 0;
-  };
+  auto kwait = [&](uint32_t bar, uint32_t parity) { mbar_wait_small(bar, parity); };
+  // the thread that issues TMA / bulk copies on behalf of the producers: a lane of warp 0 picked with elect.sync
+  auto tma_issuer = [&]() -> bool { return warp == 0 && elect_one() != 0; };
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = p.Cout / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int KT1 = p.KH * p.KW * p.cin_chunks;                 // k-tiles of the main convolution
@@ -315,11 +164,8 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
   // global memory is read and written: wait until the preceding grid has completed and flushed.  Both are no-ops otherwise.
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  // EW == 16: 768 threads x 80 registers at launch; the producer and MMA warp groups give registers to the four epilogue groups
-  // (setmaxnreg sits at the top of each role branch so that ptxas allocates every role against its own budget)
 
   if (warp < TC_PRODUCER_WARPS) {
-    if constexpr (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     // =============================================================================== producers (128 threads)
     // Coalesced gather: consecutive lanes cover one row's bytes (4 lanes x 16 B = 64 B int8 row, 2 lanes x 16 B = packed
     // 4-bit row), so a warp-level cp.async touches 8 (16) cache lines instead of 32.  Each thread serves A_PASSES rows.
@@ -379,9 +225,6 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
           for (int kh = 0; kh < 3; ++kh, it += 3) {
             // one kernel row (kw = 0, 1, 2) per iteration: three k-tiles share the barrier waits' latency, one proxy fence
             const bool vh = row_ok && (unsigned)(h + kh - 1) < (unsigned)p.H;
-            const uint32_t ptile = (tile - blockIdx.x) / gridDim.x;
-            const bool tr = (warp == 0 && kh == 1 && c == 0);
-            if (tr) trace(0, ptile, 0);
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
               const int stage = (it + kw) % STAGES;
@@ -393,7 +236,6 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
                 else tma_load_2d(smem_base + stage * S::STAGE + S::A_STAGE, &maps.b, ktile * 64, n0, full_bar(stage));
               }
             }
-            if (tr) trace(0, ptile, 1);
             constexpr int NV = A4 ? 2 : 4;                               // 16-byte vectors per patch row
             uint4 val[3][NV];
 #pragma unroll
@@ -424,19 +266,15 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
                 }
               }
             }
-            if (tr) trace(0, ptile, 2);
             fence_proxy_async();
-            if (tr) trace(0, ptile, 3);
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) mbar_arrive(full_bar((it + kw) % STAGES));
-            if (tr) trace(0, ptile, 4);
           }
           asm volatile("bar.sync 2, %0;" ::"n"(TC_PRODUCER_WARPS * 32));   // every thread is done reading this patch buffer
         }
       }
     } else if (tma_a) {
-      if constexpr (LEAN) {
-        // lean TMA producer: one lane of warp 0 chosen with elect.sync (straight-line UTMALDG / UBLKCP instead of an ELECT loop per
+        // TMA producer: one lane of warp 0 chosen with elect.sync (straight-line UTMALDG / UBLKCP instead of an ELECT loop per
         // issue), ring position tracked incrementally, the weight pointer of the channel block hoisted out of the k loop
         if (warp == 0 && elect_one()) {
           uint32_t stage = 0, phase = 0;
@@ -454,21 +292,6 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
             }
           }
         }
-      } else
-      if (tid == 0) {
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
-          for (int kt = 0; kt < KT; ++kt, ++it) {
-            const int stage = it % STAGES;
-            kwait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
-            const uint32_t a_base = smem_base + stage * S::STAGE;
-            mbar_arrive_expect_tx(full_bar(stage), S::A_STAGE + S::B_STAGE);
-            tma_load_2d(a_base, &maps.a, kt * 64, m0, full_bar(stage));
-            if (p.w_tiled) bulk_load_1d(a_base + S::A_STAGE, p.w_tiled + ((size_t)(n0 / BN) * KT1 + kt) * S::B_STAGE, S::B_STAGE, full_bar(stage));
-            else tma_load_2d(a_base + S::A_STAGE, &maps.b, kt * 64, n0, full_bar(stage));
-          }
-        }
-      }
     } else {
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;   // m fastest: weights / constants change rarely
@@ -489,12 +312,9 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
         pix2[i] = DUAL ? (n * p.H2 + ho * p.stride2) * p.W2 + wo * p.stride2 : 0;
       }
       int c = 0, kw = 0, kh = 0;
-      const uint32_t ptile = (tile - blockIdx.x) / gridDim.x;
-      if (warp == 0) trace(0, ptile, 0);
       for (int kt = 0; kt < KT; ++kt, ++it) {
         const int stage = it % STAGES;
         kwait(empty_bar(stage), ((it / STAGES) & 1) ^ 1);
-        if (warp == 0 && kt == 0) trace(0, ptile, 1);
         const uint32_t a_base = smem_base + stage * S::STAGE;
         const uint32_t b_base = a_base + S::A_STAGE;
 #pragma unroll
@@ -535,7 +355,6 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
         }
         if (++c == p.cin_chunks) { c = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
       }
-      if (warp == 0) trace(0, ptile, 2);
     }
     // drain
     cp_async_wait<0>();
@@ -544,23 +363,16 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
     fence_proxy_async();
     for (uint32_t j = pending; j > 0; --j) mbar_arrive(full_bar((it - j) % STAGES));
     }
-  } else if (warp == TC_MMA_WARP || (EW == 16 && warp < EPI_WARP0)) {
-    if constexpr (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // warps 4-7 (5-7 only donate registers)
+  } else if (warp == TC_MMA_WARP) {
     // =============================================================================== MMA issuer (one lane)
-    // LEAN: the issuing lane is chosen with elect.sync by the converged warp; nvcc then emits straight-line UTCIMMA / UTCBAR,
-    // whereas issue from a `lane == 0` branch is wrapped in an ELECT + BRA.U.ANY loop per instruction.
-    uint32_t issuer;
-    if constexpr (LEAN) issuer = elect_one();
-    else issuer = (warp == TC_MMA_WARP && lane == 0) ? 1u : 0u;
-    if (issuer) {
+    // The issuing lane is chosen with elect.sync by the converged warp.  The ring position is tracked incrementally, the
+    // shared-memory descriptors advance by constants (low word = address >> 4 | 1 << 16, the high word never changes) and the
+    // generic->async proxy fence is issued only when the A tile was written by plain cp.async (the other producers fence before
+    // they arrive, TMA needs none): ~15 SASS instructions per k-tile.
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_i8(BM, BN, !A4);   // packed 4-bit activations are unsigned
-      uint32_t it = 0, tile_iter = 0;
-      if constexpr (LEAN) {
-        // Lean issue loop (opt-in, HAWQ_B200_MMA_FAST=1).  ncu source counters (profiles/r01/experiments/README.md) show the
-        // issuing lane is the pacing resource of the REQUANT layers: ~60 dependent instructions per k-tile.  Here the ring
-        // position is tracked incrementally, the shared-memory descriptors advance by constants (low word = address >> 4 |
-        // 1 << 16, the high word never changes), the generic->async proxy fence is issued only when the A tile was written by
-        // plain cp.async (the other producers fence before they arrive, TMA needs none), and there is no tracing.
+      uint32_t tile_iter = 0;
+      {
         const bool consumer_fence = !A4 && p.tma_a == 0 && !(EPI == TC_EPI_REQ && p.patch_rows != 0);
         const uint64_t desc_hi = umma_desc_sw64(0) & 0xFFFFFFFF00000000ull;
         const uint32_t a_lo0 = (smem_base >> 4) | (1u << 16);
@@ -586,34 +398,9 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
             if (stage == STAGES) { stage = 0; phase ^= 1; a_lo = a_lo0; }
           }
         }
-      } else {
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
-        const int buf = tile_iter & 1;
-        trace(1, tile_iter, 0);
-        kwait(tempty_bar(buf), ((tile_iter >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
-        tc_fence_after();
-        trace(1, tile_iter, 1);
-        const uint32_t d_tmem0 = tmem_base + buf * ACC_STRIDE;
-        for (int kt = 0; kt < KT; ++kt, ++it) {
-          const uint32_t d_tmem = d_tmem0 + ((DUAL && kt >= KT1) ? BN : 0);     // dual mode: identity conv -> second accumulator
-          const int stage = it % STAGES;
-          kwait(full_bar(stage), (it / STAGES) & 1);
-          fence_proxy_async();            // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
-          tc_fence_after();
-          if (kt == 0) trace(1, tile_iter, 2);
-          const uint32_t a_addr = smem_base + stage * S::STAGE;
-          const uint32_t b_addr = a_addr + S::A_STAGE;
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_i8(d_tmem, umma_desc_sw64(a_addr + k * 32), umma_desc_sw64(b_addr + k * 32), idesc, (k != 0) || (kt != 0 && !(DUAL && kt == KT1)));
-          umma_commit(empty_bar(stage));                          // smem stage reusable once these MMAs retire
-          if (kt == KT - 1) { umma_commit(tfull_bar(buf)); trace(1, tile_iter, 3); }   // accumulator complete
-        }
-      }
       }
     }
   } else {
-    if constexpr (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
     // =============================================================================== epilogue (EW warps)
     const int ew = warp - EPI_WARP0;             // 0..EW-1
     const int quarter = warp & 3;                // TMEM lane quarter this warp may access
@@ -725,10 +512,8 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
         prefetch_residual(tile, rslice);
       }
 
-      if (ew == 0) trace(2, tile_iter, 0);
       kwait(tfull_bar(buf), (tile_iter >> 1) & 1);
       tc_fence_after();
-      if (ew == 0) trace(2, tile_iter, 1);
       if constexpr (EPI == TC_EPI_RES22) {
         kwait(res_bar(ew, tile_iter & 1), (tile_iter >> 1) & 1);     // residual tile landed (TMA)
         if (lane == 0) bulk_wait_read_all();                            // previous tile's TMA stores have read y / low tiles
@@ -739,7 +524,6 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
       }
       __syncwarp();
       const uint8_t* myres = rslice + lane * PITCH;
-      if (ew == 0) trace(2, tile_iter, 2);
 
 #pragma unroll
       for (int cb = 0; cb < CW; cb += 32) {
@@ -881,7 +665,6 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
-      if (ew == 0) trace(2, tile_iter, 3);
 
       const int rows_ok = p.M - (m0 + quarter * 32);
       if constexpr (S::TMA_IO) {
@@ -940,7 +723,6 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) conv_tc_kernel(const ConvPa
       }
       __syncwarp();   // staging slices are rewritten by the next tile
       }
-      if (ew == 0) trace(2, tile_iter, 4);
     }
     if constexpr (S::TMA_IO) {
       if (lane == 0) bulk_wait_all();

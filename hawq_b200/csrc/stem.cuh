@@ -104,9 +104,8 @@ __device__ __forceinline__ void stem_conv_persistent_body(const int8_t* __restri
   }
 }
 
-// PERSIST (opt-in, HAWQ_B200_STEM_PERSIST=1, not yet validated on hardware): a grid of a few CTAs per SM loops over the tiles, so the
-// 14 KB of weights and the per-channel constants are staged once per CTA instead of once per 8x16 tile (12 544 times per batch of 128).
-template <bool PERSIST = false>
+// Persistent: a grid of a few CTAs per SM loops over the 8x16 tiles, so the 14 KB of weights and the per-channel constants are
+// staged once per CTA instead of once per tile (12 544 times per batch of 128).
 __global__ void __launch_bounds__(256) stem_conv_kernel(const int8_t* __restrict__ x, const uint32_t* __restrict__ w,
                                                         const hawq_chan* __restrict__ chan, int N, int H, int W,
                                                         int Ho, int Wo, int lo, int hi, int16_t* __restrict__ out) {
@@ -115,88 +114,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const int8_t* __restrict
   __shared__ hawq_chan sChan[64];
   __shared__ double sM[64];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  if constexpr (PERSIST) {
-    stem_conv_persistent_body(x, w, chan, N, H, W, Ho, Wo, lo, hi, out, sPatch, sW, sChan, sM);
-    return;
-  }
-  const int n = blockIdx.z;
-  const int oy0 = blockIdx.y * STEM_TH, ox0 = blockIdx.x * STEM_TW;
-  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
-
-  for (int i = tid; i < 64 * 56; i += 256) sW[(i / 56) * STEM_WPITCH + (i % 56)] = w[i];
-  int slow = 0;
-  if (tid < 64) {
-    const hawq_chan c = chan[tid];
-    sChan[tid] = c;
-    sM[tid] = dyadic_to_double(c.m, c.e);
-    slow = !dyadic_is_fast(c.m, c.e);
-  }
-  for (int i = tid; i < STEM_PH * STEM_PW; i += 256) {
-    const int py = i / STEM_PW, px = i - py * STEM_PW;
-    const int iy = iy0 + py, ix = ix0 + px;
-    uint32_t v = 0;
-    if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) {
-      const int8_t* s = x + ((size_t)(n * H + iy) * W + ix) * 3;
-      v = (uint32_t)(uint8_t)s[0] | ((uint32_t)(uint8_t)s[1] << 8) | ((uint32_t)(uint8_t)s[2] << 16);
-    }
-    sPatch[i] = v;
-  }
-  const bool use_slow = __syncthreads_or(slow) != 0;
-
-  int32_t acc[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[j][k] = 0;
-
-  const int oy = warp;  // one output row (16 pixels = one m16 tile) per warp
-#pragma unroll
-  for (int kh = 0; kh < 7; ++kh) {
-    const uint32_t* prow = sPatch + (2 * oy + kh) * STEM_PW;
-    uint32_t a[4];
-    a[0] = prow[2 * g + t];
-    a[1] = prow[2 * (g + 8) + t];
-    a[2] = prow[2 * g + 4 + t];
-    a[3] = prow[2 * (g + 8) + 4 + t];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint32_t b[2];
-      const uint32_t* wr = sW + (8 * j + g) * STEM_WPITCH + kh * 8;
-      b[0] = wr[t];
-      b[1] = wr[4 + t];
-      mma_16832<false>(acc[j], a, b);
-    }
-  }
-
-  const int oyg = oy0 + oy;
-  if (oyg >= Ho) return;
-#pragma unroll
-  for (int hf = 0; hf < 2; ++hf) {
-    const int oxg = ox0 + g + hf * 8;
-    if (oxg >= Wo) continue;
-    int16_t* o = out + ((size_t)(n * Ho + oyg) * Wo + oxg) * 64;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = 8 * j + 2 * t;
-      const hawq_chan c0 = sChan[c], c1 = sChan[c + 1];
-      const int32_t v0 = sat_add(acc[j][hf * 2 + 0], c0.bias), v1 = sat_add(acc[j][hf * 2 + 1], c1.bias);
-      int32_t q0, q1;
-      if (use_slow) {
-        q0 = rhe_requant(v0, c0.m, c0.e);
-        q1 = rhe_requant(v1, c1.m, c1.e);
-      } else {
-        q0 = rhe_requant_fast(v0, sM[c]);
-        q1 = rhe_requant_fast(v1, sM[c + 1]);
-      }
-      q0 = clampi(q0, lo, hi);
-      q1 = clampi(q1, lo, hi);
-      q0 = max(q0, 0);
-      q1 = max(q1, 0);
-      *reinterpret_cast<uint32_t*>(o + c) = (uint32_t)(q0 & 0xFFFF) | ((uint32_t)(q1 & 0xFFFF) << 16);
-    }
-  }
+  stem_conv_persistent_body(x, w, chan, N, H, W, Ho, Wo, lo, hi, out, sPatch, sW, sChan, sM);
 }
 
 // nn.MaxPool2d(3, 2, 1) on the (non-negative) int16 stem output, then: residual stream y (uint16 / int32) and the

@@ -28,7 +28,8 @@ class CompiledModel:
     reference's loaders produce), or uint8 NHWC [N,H,W,3] raw pixels (ToTensor + Normalize(mean, std) + input quantisation are
     then one kernel at the head of the graph; needs ``model.quant_input``)."""
 
-    def __init__(self, model, example, use_cuda_graph=True, residual_bits=16, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    def __init__(self, model, example, use_cuda_graph=True, residual_bits=16, mean=IMAGENET_MEAN, std=IMAGENET_STD, gather=False,
+                 group=None):
         if not example.is_cuda:
             raise RuntimeError("compile_model needs a CUDA example input: the frozen path has no CPU implementation")
         self.model = model
@@ -46,8 +47,13 @@ class CompiledModel:
         self.static_in = example.clone()
         self.use_graph = use_cuda_graph
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.gather, self.group = bool(gather), group
+        if self.gather:
+            import torch.distributed as dist
+            self.all_flags = torch.zeros(dist.get_world_size(group), dtype=torch.int32, device=self.device)
         self.graphs = {}
         self.outs = {}
+        self.gathered = {}
         self.launches = {}
         self.residual_bits = residual_bits
         self.input_scale = None
@@ -82,7 +88,9 @@ class CompiledModel:
             before = ops.launch_count
             out = self._forward(bits, fast)            # warm-up: builds all parameter caches
             self.launches[key] = ops.launch_count - before
-            self._forward(bits, fast)
+            out = self._forward(bits, fast)
+            if self.gather:
+                self.gathered[key] = all_gather_logits(out, self.group)   # also initialises the NCCL communicator before capture
         # keep every module's plan (device-resident weights / per-channel parameters) alive for as long as graphs captured
         # here may replay, even if the modules drop or rebuild theirs (unfix(), load_state_dict)
         self._plans = getattr(self, "_plans", [])
@@ -99,6 +107,9 @@ class CompiledModel:
             ops.reset_status(idx)
             out = self._forward(bits, fast)
             ops.copy_status(idx, self.flag)
+            if self.gather:                     # the path's one collective rides inside the graph: no extra launch / host work per step
+                self.gathered[key] = all_gather_logits(out, self.group)
+                self._gather_flags()
         self.graphs[key] = g
         self.outs[key] = out
 
@@ -109,18 +120,40 @@ class CompiledModel:
             ops.reset_status(self.device.index)
             self.outs[key] = self._forward(self.bits_of[key], key != "safe")
             ops.copy_status(self.device.index, self.flag)
+            if self.gather:
+                self.gathered[key] = all_gather_logits(self.outs[key], self.group)
+                self._gather_flags()
         return self.outs[key]
 
+    def _gather_flags(self):
+        """Sharded runs: every rank sees every rank's status word, so all ranks take the same (exact) fallback together."""
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(self.all_flags, self.flag, group=self.group)
+
+    def _flags(self, host_flags=None):
+        if self.gather:
+            v = 0
+            for f in (self.all_flags.tolist() if host_flags is None else host_flags):
+                v |= int(f)
+            return v
+        return int(self.flag.item()) if host_flags is None else int(host_flags[0])
+
+    def _result(self, key):
+        return self.gathered[key] if self.gather else self.outs[key]
+
     def run_async(self, x=None):
-        """Enqueue one forward (no host sync, no overflow check); returns the static logits tensor."""
+        """Enqueue one forward (no host sync, no overflow check); returns the static logits tensor (with ``gather`` the logits
+        of the whole sharded batch, gathered from every rank inside the same CUDA graph)."""
         if x is not None:
             self.static_in.copy_(x, non_blocking=True)
-        return self._run(self.residual_bits)
+        out = self._run(self.residual_bits)
+        return self.gathered[self.residual_bits] if self.gather else out
 
     def __call__(self, x=None):
         """Exact forward: replays the fast graph, checks the overflow flag, falls back to int32 residuals if needed."""
         out = self.run_async(x)
-        flags = int(self.flag.item())
+        self._last_key = self.residual_bits
+        flags = self._flags()
         if flags & 2:
             raise RuntimeError("hawq_b200: HAWQ_FLAG_BAD_RATIO raised (a dyadic ratio > 1 reached the fast kernel): results invalid")
         if flags & 4:                          # a ratio > 1 term left int32 on the fast path: saturating generic kernels
@@ -128,21 +161,25 @@ class CompiledModel:
             with torch.no_grad():
                 if "safe" not in self.outs:
                     self._build(32, key="safe")
-                out = self._run("safe")
-            return out
+                self._run("safe")
+            self._last_key = "safe"
+            return self._result("safe")
         if self.residual_bits == 16 and flags & 1:
             self.fallbacks += 1
             if 32 not in self.outs:
                 with torch.no_grad():
                     self._build(32)
-            out = self._run(32)
+            self._run(32)
+            self._last_key = 32
+            return self._result(32)
         return out
 
     def run_pipelined(self, host_batches, post=None):
         """Exact forward over an iterable of pinned host batches with copy/compute overlap: the H2D copy of batch i+1 runs on a
         copy stream while batch i computes; logits and the status flags come back through pinned buffers and are checked one
         step later (a raised overflow flag re-runs that batch through ``__call__``, i.e. the exact int32 / saturating graphs).
-        ``post`` (e.g. ``all_gather_logits``) is applied to the device logits before they are read back.
+        ``post`` is applied to the device logits before they are read back.  With ``gather`` the logits of the whole sharded batch
+        stay on the device (``self.gathered``) and the host reads this rank's shard.
         Yields the host logits tensor of every batch, in order (valid until the second next iteration)."""
         dev = self.device
         main = torch.cuda.current_stream(dev)
@@ -153,7 +190,7 @@ class CompiledModel:
                 out = post(out)
             self._pipe = dict(copy=cs, stage=[torch.empty_like(self.static_in) for _ in range(2)],
                               out=[torch.empty(out.shape, dtype=out.dtype).pin_memory() for _ in range(2)],
-                              flag=[torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)],
+                              flag=[torch.zeros(self.all_flags.numel() if self.gather else 1, dtype=torch.int32).pin_memory() for _ in range(2)],
                               h2d=[torch.cuda.Event() for _ in range(2)], free=[torch.cuda.Event() for _ in range(2)],
                               done=[torch.cuda.Event() for _ in range(2)])
         P = self._pipe
@@ -161,8 +198,10 @@ class CompiledModel:
 
         def finish(slot, xb):
             P["done"][slot].synchronize()
-            if int(P["flag"][slot][0]) & 7:
-                return self(xb).to("cpu")          # rare: exact fallback path, synchronous
+            if self._flags(P["flag"][slot].tolist()) & 7:
+                self(xb)                            # rare: exact fallback path, synchronous (sharded runs: every rank takes it together)
+                out = self.outs[self._last_key]
+                return (post(out) if post is not None else out).to("cpu")
             return P["out"][slot]
 
         for i, xb in enumerate(host_batches):
@@ -178,7 +217,7 @@ class CompiledModel:
             if post is not None:
                 out = post(out)
             P["out"][slot].copy_(out, non_blocking=True)
-            P["flag"][slot].copy_(self.flag, non_blocking=True)
+            P["flag"][slot].copy_(self.all_flags if self.gather else self.flag, non_blocking=True)
             P["done"][slot].record(main)
             if prev is not None:
                 yield finish(*prev)
@@ -191,12 +230,14 @@ class CompiledModel:
         return self.launches.get(self.residual_bits, 0)
 
 
-def compile_model(model, example, use_cuda_graph=True, residual_bits=16, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+def compile_model(model, example, use_cuda_graph=True, residual_bits=16, mean=IMAGENET_MEAN, std=IMAGENET_STD, gather=False, group=None):
     """Freeze ``model`` (a QResNet or any graph built from hawq_b200.modules) and compile it for ``example``'s shape and dtype
-    (int8 NHWC, fp32 NCHW or uint8 NHWC; ``mean`` / ``std`` only matter for uint8 pixels)."""
+    (int8 NHWC, fp32 NCHW or uint8 NHWC; ``mean`` / ``std`` only matter for uint8 pixels).  ``gather``: the batch is sharded over the
+    ranks of ``group`` (torch.distributed, NCCL) and every forward all-gathers the logits inside the CUDA graph."""
     freeze_model(model)
     model.eval()
-    return CompiledModel(model, example, use_cuda_graph=use_cuda_graph, residual_bits=residual_bits, mean=mean, std=std)
+    return CompiledModel(model, example, use_cuda_graph=use_cuda_graph, residual_bits=residual_bits, mean=mean, std=std, gather=gather,
+                         group=group)
 
 
 def all_gather_logits(local_logits, group=None):

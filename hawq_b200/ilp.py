@@ -122,7 +122,7 @@ def latency_table_from_detail(detail4, detail8, arch, parameters):
     last = "quant_convbn3" if bottleneck else "quant_convbn2"
     tables = []
     for det in (detail4, detail8):
-        launches = iter([l for l in det["layers"] if l["kernel"].startswith("hawq_conv2d")])
+        launches = iter([l for l in det["layers"] if l["kernel"].startswith(("hawq_conv2d", "conv_"))])
         lat = np.zeros(len(names))
         units = sorted({n.rsplit(".", 1)[0] for n in names}, key=lambda u: [int(t) for t in u.replace("stage", "").replace("unit", "").split(".")])
         for u in units:
@@ -132,7 +132,7 @@ def latency_table_from_detail(detail4, detail8, arch, parameters):
             l = next(launches)
             if not resize:
                 lat[idx[u + "." + last]] = l["ms"]
-            elif l["kernel"] == "hawq_conv2d_dual":
+            elif l["kernel"] in ("hawq_conv2d_dual", "conv_tc_dual"):
                 a, b = idx[u + "." + last], idx[u + ".quant_identity_convbn"]
                 w = parameters[a] / (parameters[a] + parameters[b])
                 lat[a], lat[b] = l["ms"] * w, l["ms"] * (1 - w)

@@ -424,3 +424,43 @@ def test_bad_arguments_are_reported():
                    w, chan, res=x, out=x)
     with pytest.raises(RuntimeError, match="no CPU path"):
         ops.conv2d(x.cpu(), ops.conv_desc(1, 2, 2, 64, 64, 1, 1, 1, 0, 8), ops.epilogue(EPI_RAW_I32), w, chan, out=x)
+
+
+# ------------------------------------------------------------------------------------------------ conv_halo (3x3 in place)
+HALO_GEOMS = [
+    # N, H, W, Cin, Cout  (3x3 stride 1 pad 1)
+    (2, 56, 56, 64, 64),       # ResNet-50 stage 1: R = 2 rows per tile
+    (2, 28, 28, 128, 128),     # stage 2: R = 4, two 64-channel chunks, BN = 128
+    (3, 14, 14, 256, 256),     # stage 3: R = 8 -> tiles of 8 + 6 rows, BN = 64 (weights of a 128-block do not fit)
+    (3, 7, 7, 64, 128),        # one image per tile (R = H)
+    (1, 20, 12, 64, 192),      # Cout = 192: BN = 64, three channel blocks; H % R != 0
+    (5, 6, 6, 128, 128),
+    (1, 9, 30, 64, 64),        # R = 4, H = 9: last tile has one valid row
+    (2, 5, 126, 64, 64),       # widest supported row: W + 2 = 128, R = 1
+    (150, 4, 4, 64, 64),       # more tiles than SMs
+]
+
+
+@pytest.mark.parametrize("a_bits", [8, 4])
+@pytest.mark.parametrize("geom", HALO_GEOMS)
+def test_conv_halo_requant(geom, a_bits):
+    """3x3 stride-1 REQUANT layers with re-tiled weights take the in-place kernel (conv_halo.cuh): bit-exact vs the ABI model,
+    and the launch counter proves that kernel ran."""
+    from hawq_b200 import _lib
+    n, h, w, cin, cout = geom
+    r = rng(sum(v * (i + 7) for i, v in enumerate(geom)) * 8 + a_bits)
+    x = rand_act(r, n * h * w * cin, a_bits)
+    wt = torch.from_numpy(r.randint(-128 if a_bits == 8 else -8, 128 if a_bits == 8 else 8, size=(cout, 3, 3, cin)).astype(np.int8))
+    if a_bits == 4:
+        ops.permute_weights_for_i4(wt)
+    w_dev = ops.upload_weights(wt, DEV)
+    for out_bits, clamp, relu in [(8, (-128, 127), 1), (4, (0, 15), 1), (8, (-128, 127), 0)]:
+        chan = make_chan(r, cout, ratio_lo=1e-5)
+        d = ops.conv_desc(n, h, w, cin, cout, 3, 3, 1, 1, a_bits)
+        ep = ops.epilogue(EPI_REQUANT, relu=relu, out_bits=out_bits, clamp=clamp, flags=TC_FLAG)
+        before = _lib.load().hawq_debug_kernel_count(1)
+        over = dict(w=w_dev, desc=ops.conv_desc(n, h, w, cin, cout, 3, 3, 1, 1, a_bits, 1))
+        (c_out,), (g_out,) = run_both("conv2d", dict(x=x, desc=d, ep=ep, w=wt, chan=chan, out=out_buf(n * h * w * cout, out_bits)), ["out"], over)
+        assert _lib.load().hawq_debug_kernel_count(1) == before + 1, "conv_halo did not take this launch"
+        assert torch.equal(c_out, g_out), (geom, a_bits, out_bits)
+        assert ops.get_status(0) == 0

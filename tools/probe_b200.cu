@@ -132,11 +132,10 @@ void run_desc() {
 // cp.async.bulk; a consumer thread only waits and releases.  mode 0: CTA-distinct chunks walking a `span`-byte region;
 // mode 1: all CTAs read the same sequence of chunks (weights-like);  CL > 1: mode 1 with cluster multicast (one CTA issues 1/CL of the bytes
 // to all CTAs of the cluster).
-template <int CL>
+template <int CL, int STAGES = 8>
 __global__ void __launch_bounds__(64, 1) probe_l2(const uint8_t* __restrict__ src, size_t span, int chunk, int iters, int mode, unsigned long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
-  constexpr int STAGES = 8;
   __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
   uint32_t rank = 0;
   if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -185,27 +184,59 @@ __global__ void __launch_bounds__(64, 1) probe_l2(const uint8_t* __restrict__ sr
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = 1;
 }
 
-template <int CL>
+// latency of ONE bulk copy (issue -> mbarrier completes), idle chip (grid 1) or every SM doing the same (grid 148)
+__global__ void __launch_bounds__(32, 1) probe_lat(const uint8_t* __restrict__ src, int chunk, int reps, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+    long long tot = 0;
+    for (int i = 0; i < reps; ++i) {
+      const long long t0 = clock64();
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(chunk) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(smem)), "l"(src + ((size_t)blockIdx.x * 64 + i) * chunk), "r"(chunk), "r"(smem_u32(&bar)) : "memory");
+      while (!try_wait(smem_u32(&bar), i & 1)) {}
+      tot += clock64() - t0;
+    }
+    if (blockIdx.x == 0) out[0] = tot / reps;
+  }
+}
+void run_lat(const uint8_t* src, int chunk, int grid) {
+  long long* d; CK(cudaMalloc(&d, 8));
+  CK(cudaFuncSetAttribute(probe_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, chunk + 1024));
+  probe_lat<<<grid, 32, chunk + 1024>>>(src, chunk, 64, d);
+  CK(cudaDeviceSynchronize());
+  probe_lat<<<grid, 32, chunk + 1024>>>(src, chunk, 64, d);
+  CK(cudaDeviceSynchronize());
+  long long cyc; CK(cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost));
+  printf("C: one bulk copy of %5d B at a time, %3d CTAs: %lld cycles issue -> complete (L2-resident source)\n", chunk, grid, cyc);
+  cudaFree(d);
+}
+
+template <int CL, int STAGES = 8>
 void run_l2(const uint8_t* src, size_t span, int chunk, int mode, const char* what, int grid) {
   unsigned long long* d; CK(cudaMalloc(&d, 8));
-  const int smem = 8 * chunk + 1024;
-  CK(cudaFuncSetAttribute(probe_l2<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int smem = STAGES * chunk + 1024;
+  CK(cudaFuncSetAttribute((probe_l2<CL, STAGES>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   const int iters = 4000;
-  CK(cudaLaunchKernelEx(&cfg, probe_l2<CL>, src, span, chunk, 400, mode, d));
+  CK(cudaLaunchKernelEx(&cfg, (probe_l2<CL, STAGES>), src, span, chunk, 400, mode, d));
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  CK(cudaLaunchKernelEx(&cfg, probe_l2<CL>, src, span, chunk, iters, mode, d));
+  CK(cudaLaunchKernelEx(&cfg, (probe_l2<CL, STAGES>), src, span, chunk, iters, mode, d));
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   const double bytes = (double)grid * iters * chunk;
-  printf("B: %-44s grid %3d cluster %d chunk %5d B span %4zu MB: %.2f TB/s into shared memory (%.1f GB/s per SM)\n", what, grid, CL, chunk, span >> 20, bytes / (ms * 1e-3) / 1e12,
+  printf("B: %-44s grid %3d cluster %d stages %2d chunk %5d B span %4zu MB: %.2f TB/s into shared memory (%.1f GB/s per SM)\n", what, grid, CL, STAGES, chunk, span >> 20, bytes / (ms * 1e-3) / 1e12,
          bytes / (ms * 1e-3) / 1e9 / grid);
   cudaFree(d);
 }
@@ -213,9 +244,7 @@ void run_l2(const uint8_t* src, size_t span, int chunk, int mode, const char* wh
 int main() {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("%s, %d SMs, L2 %d MB\n", prop.name, prop.multiProcessorCount, prop.l2CacheSize >> 20);
-  run_desc<64>();
-  run_desc<128>();
-  run_desc<32>();
+  if (getenv("PROBE_DESC")) { run_desc<64>(); run_desc<128>(); run_desc<32>(); }
   uint8_t* src; const size_t cap = 512ull << 20;
   CK(cudaMalloc(&src, cap)); CK(cudaMemset(src, 1, cap));
   for (int chunk : {8192, 16384, 24576}) {
@@ -226,5 +255,14 @@ int main() {
   run_l2<2>(src, 2ull << 20, 16384, 1, "same chunks, multicast pairs", 148);
   run_l2<4>(src, 2ull << 20, 16384, 1, "same chunks, multicast clusters of 4", 148);
   run_l2<1>(src, 32ull << 20, 16384, 0, "distinct chunks, L2-resident, half the SMs", 74);
+  run_l2<1, 2>(src, 32ull << 20, 8192, 0, "distinct chunks, L2-resident", 148);
+  run_l2<1, 4>(src, 32ull << 20, 8192, 0, "distinct chunks, L2-resident", 148);
+  run_l2<1, 16>(src, 32ull << 20, 8192, 0, "distinct chunks, L2-resident", 148);
+  run_l2<1, 24>(src, 32ull << 20, 8192, 0, "distinct chunks, L2-resident", 148);
+  run_l2<1, 16>(src, 32ull << 20, 4096, 0, "distinct chunks, L2-resident", 148);
+  run_l2<1, 4>(src, 32ull << 20, 32768, 0, "distinct chunks, L2-resident", 148);
+  run_l2<1, 6>(src, 32ull << 20, 32768, 0, "distinct chunks, L2-resident", 148);
+  run_l2<1, 16>(src, 512ull << 20, 8192, 0, "distinct chunks, HBM-sized", 148);
+  for (int chunk : {1024, 8192, 16384, 32768}) { run_lat(src, chunk, 1); run_lat(src, chunk, 148); }
   return 0;
 }

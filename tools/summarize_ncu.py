@@ -4,11 +4,12 @@
 usage: python tools/summarize_ncu.py gpurun_out/launches.csv "<command that was profiled>" [--json out.json] [--skip-first N]
 
 Prints per-kernel launch counts, total time and share (cold-cache, serialised: compare shares, not absolutes) and, when the
-DRAM byte counters are present, measured DRAM traffic per launch.  --json writes the conv_tc_kernel family numbers that
-bench.py reports as roofline.traffic (measured bytes per launch of the dominant kernel).
+DRAM byte counters are present, measured DRAM traffic per launch.  --json writes, per convolution kernel family and tagged with the
+digest of the build that was profiled, the numbers bench.py reports as roofline.traffic (entries of another build are ignored).
 """
 import csv
 import json
+import os
 import re
 import sys
 from collections import OrderedDict
@@ -51,20 +52,31 @@ def main():
         if have_dram:
             line += "  dram_MB/launch rd=%8.2f wr=%8.2f" % (a["rd"] / a["launches"] / 1e6, a["wr"] / a["launches"] / 1e6)
         print(line)
-    fam = {"launches": 0, "us": 0.0, "rd": 0.0, "wr": 0.0}
+    fams = OrderedDict()
     for k, a in agg.items():
-        if "conv_tc_kernel" in k:
-            for key in fam:
-                fam[key] += a[key]
-    if fam["launches"]:
-        print("conv_tc_kernel family: launches=%d share=%.1f%%" % (fam["launches"], 100 * fam["us"] / total)
+        name = "conv_tc_kernel" if "conv_tc_kernel" in k else "conv_halo_kernel" if "conv_halo_kernel" in k else None
+        if name is None:
+            continue
+        fam = fams.setdefault(name, {"launches": 0, "us": 0.0, "rd": 0.0, "wr": 0.0})
+        for key in fam:
+            fam[key] += a[key]
+    for name, fam in fams.items():
+        print("%s family: launches=%d share=%.1f%%" % (name, fam["launches"], 100 * fam["us"] / total)
               + ("  measured DRAM bytes/launch = %.1f MB (read %.1f + write %.1f)" % ((fam["rd"] + fam["wr"]) / fam["launches"] / 1e6,
                  fam["rd"] / fam["launches"] / 1e6, fam["wr"] / fam["launches"] / 1e6) if have_dram else ""))
-    if out_json and fam["launches"] and have_dram:
+    if out_json and fams and have_dram:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from hawq_b200.build import OUT
+        try:
+            build = open(OUT + ".stamp").read().strip()[:16]
+        except OSError:
+            build = None
         with open(out_json, "w") as f:
-            json.dump({"command": cmd, "kernel": "conv_tc_kernel", "launches": fam["launches"], "share_of_listed_time": fam["us"] / total,
-                       "dram_bytes_read_per_launch": fam["rd"] / fam["launches"], "dram_bytes_write_per_launch": fam["wr"] / fam["launches"],
-                       "traffic_bytes_per_launch": (fam["rd"] + fam["wr"]) / fam["launches"]}, f, indent=1)
+            json.dump({"command": cmd, "build": build,
+                       "kernels": {name: {"launches": fam["launches"], "share_of_listed_time": fam["us"] / total,
+                                          "dram_bytes_read_per_launch": fam["rd"] / fam["launches"],
+                                          "dram_bytes_write_per_launch": fam["wr"] / fam["launches"],
+                                          "traffic_bytes_per_launch": (fam["rd"] + fam["wr"]) / fam["launches"]} for name, fam in fams.items()}}, f, indent=1)
 
 
 if __name__ == "__main__":
