@@ -311,10 +311,10 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
   if (tc_enabled && tc_epi && folds && (ratios_one || ratios_wide)) {
     const bool a4 = d->a_bits == 4;
     // 3x3 stride-1 REQUANT layers: A operand read in place from a zero-padded TMA patch, weights stationary (conv_halo.cuh)
-    if (d->w_layout == 1 && ep->mode == HAWQ_EPI_REQUANT) {
-      const int hr = launch_conv_halo(h->sm_count, d, ep, x, w + (size_t)d->Cout * p.K, chan, out, h->status, stream);
+    if (ep->mode == HAWQ_EPI_REQUANT) {
+      const int hr = launch_conv_halo(h->sm_count, d, ep, x, w, chan, out, h->status, stream);
       if (hr < 0) return fail(hr, "%s", halo_last_error());
-      if (hr == 0) { ++g_kernel_count[1]; return launch_check("conv_halo"); }
+      if (hr == 0 || hr == 2) { ++g_kernel_count[1]; g_kernel_count[2] += hr == 2; return launch_check("conv_halo"); }
     }
     ++g_kernel_count[0];
     const int bn = (d->Cout % 128 == 0) ? 128 : 64;

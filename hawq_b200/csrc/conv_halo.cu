@@ -39,7 +39,6 @@ static bool plan_for(int bn, bool a4, int K, int wp, int R, HaloPlan* out) {
   const int b_bytes = (K / 64) * bn * 64;
   const int patch_alloc = round_up((128 + 2 * wp + 2) * 64, 1024);
   const int packed_alloc = a4 ? round_up((R + 2) * wp * 32, 1024) : 0;
-  const int stage = 8 * 32 * (bn / 2 + 16);
   const int cst = bn * 16;
   const int bars = 256;
   for (int npb = a4 ? 2 : HALO_MAX_BUFS; npb >= 2; --npb) {
@@ -48,7 +47,6 @@ static bool plan_for(int bn, bool a4, int K, int wp, int R, HaloPlan* out) {
     HaloParams& p = out->p;
     p.off_patch = off; off += npb * patch_alloc;
     p.off_packed = off; off += nkb * packed_alloc;
-    p.off_stage = off; off += stage;
     p.off_cst = off; off += cst;
     p.off_bar = off; off += bars;
     const int total = off + 1024;      // slack for the 1024-byte alignment of the base
@@ -74,12 +72,12 @@ int halo_set_attributes() {
 }
 
 template <int BN, bool A4>
-static void launch(const HaloPlan& plan, const CUtensorMap& map, int grid, cudaStream_t st) {
+static void launch(const HaloPlan& plan, const CUtensorMap& map, const CUtensorMap& wmap, int grid, cudaStream_t st) {
   static const bool pdl = [] { const char* e = getenv("HAWQ_B200_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(HALO_THREADS, 1, 1);
+  cfg.blockDim = dim3(halo_threads(A4), 1, 1);
   cfg.dynamicSmemBytes = (size_t)plan.total;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -87,14 +85,14 @@ static void launch(const HaloPlan& plan, const CUtensorMap& map, int grid, cudaS
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, A4>, plan.p, map);
+  cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, A4>, plan.p, map, wmap);
 }
 
-int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x, const int8_t* w_tiled,
+int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x, const int8_t* w_ohwi,
                      const hawq_chan* chan, void* out, int32_t* status, void* stream) {
-  static const int mode = [] { const char* e = getenv("HAWQ_B200_HALO"); return e ? atoi(e) : 1; }();   // 0: off; 2: with the descriptor base-offset field
-  if (!mode) return 1;
-  if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1 || d->w_layout != 1) return 1;
+  static const bool enabled = [] { const char* e = getenv("HAWQ_B200_HALO"); return !(e && e[0] == '0'); }();   // debugging switch
+  if (!enabled) return 1;
+  if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1) return 1;
   if (ep->mode != HAWQ_EPI_REQUANT || (ep->out_bits != 8 && ep->out_bits != 4) || !(ep->flags & HAWQ_EP_RATIOS_LE_ONE)) return 1;
   const int wp = d->W + 2;
   if (wp > 128 || wp > 256) return 1;
@@ -105,7 +103,6 @@ int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_
   memset(&plan, 0, sizeof(plan));
   if (!((d->Cout % 128 == 0 && plan_for(128, a4, K, wp, R, &plan)) || plan_for(64, a4, K, wp, R, &plan))) return 1;
   HaloParams& p = plan.p;
-  p.w_tiled = w_tiled; p.tiled_bn = (d->Cout % 128 == 0) ? 128 : 64;
   p.chan = chan; p.out = (uint8_t*)out; p.status = status;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cout = d->Cout; p.chunks = d->Cin / 64; p.R = R; p.wp = wp;
   p.tiles_per_img = (d->H + R - 1) / R;
@@ -118,7 +115,6 @@ int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_
   p.ctas_per_n = per_n;
   p.patch_bytes = (R + 2) * wp * (a4 ? 32 : 64);
   p.relu = ep->relu; p.out_bits = ep->out_bits; p.lo = ep->clamp_lo; p.hi = ep->clamp_hi;
-  p.desc_bo = mode == 2 ? 1 : 0;
 
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) { snprintf(g_halo_err, sizeof(g_halo_err), "conv_halo: cuTensorMapEncodeTiled unavailable"); return HAWQ_ERR_CUDA; }
@@ -132,11 +128,30 @@ int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_
                          a4 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { snprintf(g_halo_err, sizeof(g_halo_err), "conv_halo: cuTensorMapEncodeTiled failed (%d)", (int)r); return HAWQ_ERR_CUDA; }
 
+  // weights [Cout][3][3][Cin] int8 as {Cin bytes, Cout rows (pitch 9 * Cin), 9 taps (pitch Cin)}: box {64, BN, 9}
+  CUtensorMap wmap;
+  const cuuint64_t wdims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Cout, 9};
+  const cuuint64_t wstrides[2] = {(cuuint64_t)K, (cuuint64_t)d->Cin};
+  const cuuint32_t wbox[3] = {64u, (cuuint32_t)plan.bn, 9u};
+  const cuuint32_t westr[3] = {1, 1, 1};
+  const CUresult rw = enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(w_ohwi), wdims, wstrides, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  p.w_rank3 = 1;
+  if (rw != CUDA_SUCCESS) {        // plain matrix view [Cout][K], box {64, BN}
+    const cuuint64_t mdims[2] = {(cuuint64_t)K, (cuuint64_t)d->Cout};
+    const cuuint64_t mstrides[1] = {(cuuint64_t)K};
+    const cuuint32_t mbox[2] = {64u, (cuuint32_t)plan.bn};
+    const CUresult r2 = enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(w_ohwi), mdims, mstrides, mbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r2 != CUDA_SUCCESS) { snprintf(g_halo_err, sizeof(g_halo_err), "conv_halo: cuTensorMapEncodeTiled (weights) failed (%d, %d)", (int)rw, (int)r2); return HAWQ_ERR_CUDA; }
+    p.w_rank3 = 0;
+  }
+
   const int grid = p.n_tiles * p.ctas_per_n;
   cudaStream_t st = (cudaStream_t)stream;
-  if (plan.bn == 128) { if (a4) launch<128, true>(plan, map, grid, st); else launch<128, false>(plan, map, grid, st); }
-  else { if (a4) launch<64, true>(plan, map, grid, st); else launch<64, false>(plan, map, grid, st); }
-  return 0;
+  if (plan.bn == 128) { if (a4) launch<128, true>(plan, map, wmap, grid, st); else launch<128, false>(plan, map, wmap, grid, st); }
+  else { if (a4) launch<64, true>(plan, map, wmap, grid, st); else launch<64, false>(plan, map, wmap, grid, st); }
+  return p.w_rank3 ? 0 : 2;
 }
 
 }  // namespace hawq

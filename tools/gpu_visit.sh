@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 for what in "$@"; do
   case $what in
     probe)
-      nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/probe_b200 tools/probe_b200.cu && timeout 200 /tmp/probe_b200 > gpurun_out/probe_b200.txt 2>&1
+      nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/probe_b200 tools/probe_b200.cu && PROBE_TMA_ONLY=${PROBE_TMA_ONLY:-} timeout 200 /tmp/probe_b200 > gpurun_out/probe_b200.txt 2>&1
       echo "probe exit $?"; tail -30 gpurun_out/probe_b200.txt;;
     halo)
       timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "halo" > gpurun_out/pytest_halo.log 2>&1

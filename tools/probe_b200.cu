@@ -241,12 +241,96 @@ void run_l2(const uint8_t* src, size_t span, int chunk, int mode, const char* wh
   cudaFree(d);
 }
 
+
+// ------------------------------------------------------------------------------------------------ D
+// 2-D tensor TMA: boxes of `rows` x INNER bytes (SWIZZLE matching INNER) streamed into an 8-deep ring by NPROD producer threads
+// (one per warp, round robin over the stages).  Answers: what does a 64-byte inner row cost against a 128-byte one, and does a
+// second issuing warp raise the per-SM copy rate?
+#include <cuda.h>
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+template <int NPROD>
+__global__ void __launch_bounds__(32 * (NPROD + 1), 1) probe_tma(const __grid_constant__ CUtensorMap map, int box_bytes, int box_rows, int total_rows, int iters, unsigned long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+  constexpr int STAGES = 8;
+  __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&empty[s])));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nboxes = total_rows / box_rows;
+  const int stage_bytes = (box_bytes + 1023) / 1024 * 1024;
+  if (warp < NPROD && lane == 0) {
+    for (int it = warp; it < iters; it += NPROD) {
+      const int s = it % STAGES;
+      wait_bar(smem_u32(&empty[s]), ((it / STAGES) & 1) ^ 1);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(box_bytes) : "memory");
+      const int b = (blockIdx.x + it * gridDim.x) % nboxes;
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                   ::"r"(smem_u32(smem + s * stage_bytes)), "l"(reinterpret_cast<uint64_t>(&map)), "r"(0), "r"(b * box_rows), "r"(smem_u32(&full[s])) : "memory");
+    }
+  } else if (warp == NPROD && lane == 0) {
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      wait_bar(smem_u32(&full[s]), (it / STAGES) & 1);
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = 1;
+}
+template <int NPROD>
+void run_tma(uint8_t* src, int inner, int rows) {
+  static encode_tiled_fn enc = [] {
+    void* ptr = nullptr; cudaDriverEntryPointQueryResult q;
+    cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q);
+    return reinterpret_cast<encode_tiled_fn>(ptr);
+  }();
+  const int total_rows = (32 << 20) / inner;
+  CUtensorMap map;
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)total_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)inner};
+  const cuuint32_t box[2] = {(cuuint32_t)inner, (cuuint32_t)rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : inner == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  if (!enc || enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("D: encode failed\n"); return; }
+  unsigned long long* d; CK(cudaMalloc(&d, 8));
+  const int box_bytes = inner * rows;
+  const int smem = 8 * ((box_bytes + 1023) / 1024 * 1024) + 1024;
+  CK(cudaFuncSetAttribute(probe_tma<NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int iters = 4000;
+  probe_tma<NPROD><<<148, 32 * (NPROD + 1), smem>>>(map, box_bytes, rows, total_rows, 400, d);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  probe_tma<NPROD><<<148, 32 * (NPROD + 1), smem>>>(map, box_bytes, rows, total_rows, iters, d);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  const double bytes = 148.0 * iters * box_bytes;
+  printf("D: tensor TMA box %3d B x %3d rows (%5d B), %d issuing warp(s): %.2f TB/s, %.0f ns per box per SM, %.1f ns per box row\n", inner, rows, box_bytes, NPROD,
+         bytes / (ms * 1e-3) / 1e12, ms * 1e6 / iters, ms * 1e6 / iters / rows);
+  cudaFree(d);
+}
+
 int main() {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("%s, %d SMs, L2 %d MB\n", prop.name, prop.multiProcessorCount, prop.l2CacheSize >> 20);
   if (getenv("PROBE_DESC")) { run_desc<64>(); run_desc<128>(); run_desc<32>(); }
   uint8_t* src; const size_t cap = 512ull << 20;
   CK(cudaMalloc(&src, cap)); CK(cudaMemset(src, 1, cap));
+  run_tma<1>(src, 64, 128); run_tma<1>(src, 64, 232); run_tma<1>(src, 128, 64); run_tma<1>(src, 128, 116); run_tma<1>(src, 128, 232);
+  run_tma<1>(src, 32, 232); run_tma<1>(src, 64, 32); run_tma<1>(src, 128, 16);
+  run_tma<2>(src, 64, 128); run_tma<2>(src, 64, 232); run_tma<4>(src, 64, 128); run_tma<2>(src, 128, 64);
+  if (getenv("PROBE_TMA_ONLY")) return 0;
   for (int chunk : {8192, 16384, 24576}) {
     run_l2<1>(src, 32ull << 20, chunk, 0, "distinct chunks, L2-resident region", 148);
     run_l2<1>(src, 512ull << 20, chunk, 0, "distinct chunks, HBM-sized region", 148);

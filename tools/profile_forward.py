@@ -20,8 +20,7 @@ a = ap.parse_args()
 q = hb.build_synthetic_qresnet(a.arch, a.scheme, calib_batch=2)
 s_in = float(q.quant_input.current_scale())
 x = torch.clamp(torch.round(torch.randn(a.batch, 224, 224, 3) / s_in), -128, 127).to(torch.int8).cuda()
-qtensor.config.residual_bits = a.residual_bits
-with torch.no_grad():
+with torch.no_grad(), qtensor.engine_mode(residual_bits=a.residual_bits, checked=True):
     for _ in range(a.forwards):
         n, h, w, c = x.shape
         out = q(IntActivation(Node("int", (n, c, h, w), data=x.view(-1), bits=8, signed=True), x.device))
