@@ -80,6 +80,7 @@ SIGNATURES = {
     "hawq_permute_weights_for_i4": (_i32, [_vp, _i64, _i32]),
     "hawq_retile_weights": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "hawq_debug_kernel_count": (_i64, [_i32]),
+    "hawq_debug_halo_trace": (_i32, [_vp, _i32]),
     "hawq_workspace_bytes": (_i64, [C.POINTER(hawq_conv_desc), C.POINTER(hawq_epilogue_desc)]),
 }
 

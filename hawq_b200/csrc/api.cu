@@ -637,6 +637,8 @@ int hawq_retile_weights(hawq_handle* h, const int8_t* w_ohwi, int32_t Cout, int6
   return launch_check("retile_weights");
 }
 
+int32_t hawq_debug_halo_trace(int64_t* host_out, int32_t n) { return halo_read_trace(reinterpret_cast<long long*>(host_out), n); }
+
 int64_t hawq_debug_kernel_count(int32_t family) { return (family >= 0 && family < 4) ? g_kernel_count[family] : -1; }
 
 }  // extern "C"

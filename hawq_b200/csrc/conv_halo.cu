@@ -9,6 +9,15 @@
 namespace hawq {
 
 static thread_local char g_halo_err[256] = "";
+static long long* g_halo_trace = nullptr;      // device buffer [3][64][4], allocated on first use when HAWQ_B200_HALO_TRACE=1
+
+int halo_read_trace(long long* host_out, int n) {
+  if (!g_halo_trace) return 0;
+  if (n > 3 * 64 * 4) n = 3 * 64 * 4;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host_out, g_halo_trace, sizeof(long long) * n, cudaMemcpyDeviceToHost);
+  return n;
+}
 const char* halo_last_error() { return g_halo_err; }
 
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -64,7 +73,11 @@ int halo_set_attributes() {
   if ((e = cudaFuncSetAttribute(conv_halo_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess ||
       (e = cudaFuncSetAttribute(conv_halo_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess ||
       (e = cudaFuncSetAttribute(conv_halo_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(conv_halo_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess) {
+      (e = cudaFuncSetAttribute(conv_halo_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_halo_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_halo_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_halo_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_halo_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_MAX)) != cudaSuccess) {
     snprintf(g_halo_err, sizeof(g_halo_err), "conv_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return HAWQ_ERR_CUDA;
   }
@@ -85,7 +98,8 @@ static void launch(const HaloPlan& plan, const CUtensorMap& map, const CUtensorM
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, A4>, plan.p, map, wmap);
+  if (plan.p.trace) cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, A4, true>, plan.p, map, wmap);
+  else cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, A4, false>, plan.p, map, wmap);
 }
 
 int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x, const int8_t* w_ohwi,
@@ -116,6 +130,10 @@ int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_
   p.patch_bytes = (R + 2) * wp * (a4 ? 32 : 64);
   p.relu = ep->relu; p.out_bits = ep->out_bits; p.lo = ep->clamp_lo; p.hi = ep->clamp_hi;
 
+  static const bool tracing = [] { const char* e = getenv("HAWQ_B200_HALO_TRACE"); return e && e[0] == '1'; }();
+  if (tracing && !g_halo_trace) { cudaMalloc(&g_halo_trace, sizeof(long long) * 3 * 64 * 4); }
+  if (tracing) cudaMemsetAsync(g_halo_trace, 0, sizeof(long long) * 3 * 64 * 4, (cudaStream_t)stream);
+  p.trace = tracing ? g_halo_trace : nullptr;
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) { snprintf(g_halo_err, sizeof(g_halo_err), "conv_halo: cuTensorMapEncodeTiled unavailable"); return HAWQ_ERR_CUDA; }
   CUtensorMap map;

@@ -44,6 +44,7 @@ struct HaloParams {
   int packed_alloc;          // A4: bytes per packed patch buffer (multiple of 1024)
   int npb, nkb;              // int8 patch buffers, packed patch buffers (A4)
   int relu, out_bits, lo, hi;
+  long long* trace;          // debug timeline (hawq_debug_halo_trace): [3 roles][64][4] clock64 stamps of CTA 0, or null
   int w_rank3;               // weights tensor map: 1 = {Cin, Cout, 9 taps} 3-D view, 0 = plain [Cout][K] matrix
   int off_patch, off_packed, off_cst, off_bar;   // shared-memory carve-up (bytes from the 1024-aligned base; weights at 0)
 };
@@ -65,7 +66,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap
                ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 
-template <int BN, bool A4>
+template <int BN, bool A4, bool TRACE = false>
 __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap xmap,
                                                                         const __grid_constant__ CUtensorMap wmap) {
   constexpr int B_STAGE = BN * 64;
@@ -89,6 +90,14 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_bar + 8 * (5 + 4 * HALO_MAX_BUFS));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  auto stamp = [&](int role, uint32_t idx, int ev) {
+    if constexpr (TRACE) {
+      if (blockIdx.x == 0 && idx < 64) p.trace[(role * 64 + idx) * 4 + ev] = clock64();
+    }
+  };
+  // tiles of this CTA: mt = slot, slot + ctas_per_n, ...; (image, row group) advance incrementally (no division per tile)
+  const int step_n = p.ctas_per_n / p.tiles_per_img, step_t = p.ctas_per_n - step_n * p.tiles_per_img;
+  const int my_tiles = (blockIdx.x / p.n_tiles < p.m_tiles) ? (p.m_tiles - 1 - blockIdx.x / p.n_tiles) / p.ctas_per_n + 1 : 0;
   const int nt = blockIdx.x % p.n_tiles, slot = blockIdx.x / p.n_tiles;
   const int n0 = nt * BN;
   const int KT = 9 * p.chunks;
@@ -132,21 +141,26 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if constexpr (!A4) {
       if (warp == 0 && elect_one()) {
-        uint32_t b = 0, ph = 0;
-        for (int mt = slot; mt < p.m_tiles; mt += p.ctas_per_n) {
-          const int n_img = mt / p.tiles_per_img, y0 = (mt - n_img * p.tiles_per_img) * p.R;
-          for (int c = 0; c < p.chunks; ++c) {
+        uint32_t b = 0, ph = 0, g = 0;
+        int n_img = slot / p.tiles_per_img, ti = slot - n_img * p.tiles_per_img;
+        for (int t = 0; t < my_tiles; ++t) {
+          const int y0 = ti * p.R;
+          for (int c = 0; c < p.chunks; ++c, ++g) {
+            stamp(0, g, 0);
             mbar_wait_small(pempty(b), ph ^ 1);
+            stamp(0, g, 1);
             mbar_arrive_expect_tx(pfull(b), (uint32_t)p.patch_bytes);
             tma_load_4d(smem_base + p.off_patch + b * p.patch_alloc, &xmap, c * 64, -1, y0 - 1, n_img, pfull(b));
+            stamp(0, g, 2);
             if (++b == (uint32_t)p.npb) { b = 0; ph ^= 1; }
           }
+          n_img += step_n; ti += step_t;
+          if (ti >= p.tiles_per_img) { ti -= p.tiles_per_img; ++n_img; }
         }
       }
     } else {
       // packed 4-bit patches: TMA -> packed buffer (rows of 32 B, SWIZZLE_32B) -> expanded by these 128 threads into the int8
       // patch (rows of 64 B, SWIZZLE_64B) in the K order the permuted weights expect (per 32-channel block: low nibbles, high nibbles)
-      const int my_tiles = (slot < p.m_tiles) ? (p.m_tiles - 1 - slot) / p.ctas_per_n + 1 : 0;
       const int total_g = my_tiles * p.chunks;
       const int rows = p.patch_bytes / 32;
       auto issue = [&](int g) {            // one elected lane of warp 0
@@ -193,35 +207,47 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
     // =============================================================================== MMA issuer
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (elect_one()) {
+      // This thread's instruction stream paces the kernel (18 MMAs per 64-channel chunk against ~38-64 tensor cycles each), so the
+      // loop body is stripped to one add per descriptor: descriptors are handled in their own units (address >> 4, constant high
+      // word), the nine tap shifts are loop-invariant registers, weight blocks advance by immediates.  A row-shifted start address
+      // needs no base-offset field: the swizzle is a function of the shared-memory address bits.
       const uint32_t idesc = umma_idesc_i8(128, BN, !A4);     // packed 4-bit activations are unsigned
-      const uint64_t desc_hi = umma_desc_sw64(0) & 0xFFFFFFFF00000000ull;
-      // row-shifted start addresses need no base-offset field: the swizzle is a function of the address bits
-      auto desc = [&](uint32_t addr) { return desc_hi | (uint64_t)(((addr >> 4) & 0x3FFFu) | (1u << 16)); };
+      const uint32_t desc_hi = (uint32_t)(umma_desc_sw64(0) >> 32);
+      constexpr uint32_t BU = B_STAGE >> 4;                    // one weight block in descriptor units
+      uint32_t tap[9];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) tap[kh * 3 + kw] = (uint32_t)(kh * p.wp + kw) * 4u;
+      const uint32_t patch0 = ((smem_base + p.off_patch) >> 4) | (1u << 16), patch_step = (uint32_t)p.patch_alloc >> 4;
+      const uint32_t w0 = (smem_base >> 4) | (1u << 16);
       mbar_wait_small(b_full, 0);
-      uint32_t b = 0, ph = 0, tile_iter = 0;
-      for (int mt = slot; mt < p.m_tiles; mt += p.ctas_per_n, ++tile_iter) {
-        const uint32_t buf = tile_iter & 1;
-        mbar_wait_small(tempty(buf), ((tile_iter >> 1) & 1) ^ 1);
+      uint32_t b = 0, ph = 0, g = 0, a0 = patch0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const uint32_t buf = t & 1;
+        stamp(1, g, 0);
+        mbar_wait_small(tempty(buf), ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int c = 0; c < p.chunks; ++c) {
+        uint32_t wl = w0;
+        for (int c = 0; c < p.chunks; ++c, ++g) {
+          stamp(1, g, 1);
           mbar_wait_small(pfull(b), ph);
           tc_fence_after();
-          const uint32_t patch = smem_base + p.off_patch + b * p.patch_alloc;
-          uint32_t wblk = smem_base + (uint32_t)c * 9u * B_STAGE;    // weight blocks [c][tap]
+          stamp(1, g, 2);
+          if (c == 0) umma_i8_lohi<false>(d_tmem, a0 + tap[0], wl, desc_hi, idesc);
+          else umma_i8_lohi<true>(d_tmem, a0 + tap[0], wl, desc_hi, idesc);
+          umma_i8_lohi<true>(d_tmem, a0 + tap[0] + 2, wl + 2, desc_hi, idesc);
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const uint32_t a_addr = patch + (uint32_t)(kh * p.wp + kw) * 64u;
-              const uint64_t bd = desc_hi | (uint64_t)((wblk >> 4) | (1u << 16));
-              umma_i8(d_tmem, desc(a_addr), bd, idesc, (c | kh | kw) != 0 ? 1u : 0u);
-              umma_i8(d_tmem, desc(a_addr + 32), bd + 2, idesc, 1u);
-              wblk += B_STAGE;
-            }
+          for (int k = 1; k < 9; ++k) {
+            umma_i8_lohi<true>(d_tmem, a0 + tap[k], wl + k * BU, desc_hi, idesc);
+            umma_i8_lohi<true>(d_tmem, a0 + tap[k] + 2, wl + k * BU + 2, desc_hi, idesc);
           }
           umma_commit(pempty(b));
-          if (++b == (uint32_t)p.npb) { b = 0; ph ^= 1; }
+          stamp(1, g, 3);
+          wl += 9 * BU;
+          a0 += patch_step;
+          if (++b == (uint32_t)p.npb) { b = 0; ph ^= 1; a0 = patch0; }
         }
         umma_commit(tfull(buf));
       }
@@ -251,28 +277,17 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
     const int y = pos / p.wp, x = pos - y * p.wp;
     const bool row_ok = pos < p.R * p.wp && x < p.W;
     const int c0 = n0 + cg * CW;
+    // output address of this thread's row: tile base (image, first row of the group) + a per-thread constant
     const size_t row_off = (((size_t)y * p.W + x) * p.Cout + c0) * p.out_bits >> 3;
+    const size_t img_bytes = ((size_t)p.H * p.W * p.Cout * p.out_bits) >> 3, grp_bytes = ((size_t)p.R * p.W * p.Cout * p.out_bits) >> 3;
     const double2* cst = sCst + cg * CW;
-    auto pack4_sat = [&](int a, int b, int c, int d) -> uint32_t {     // bytes a, b, c, d (a lowest), clamped
-      uint32_t hi, out;
-      if (clamp_mode == 1) {
-        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
-        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(b), "r"(a), "r"(hi));
-        return __vminu4(out, hi4);
-      } else if (clamp_mode == 2) {
-        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
-        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(b), "r"(a), "r"(hi));
-        return out;
-      }
-      a = clampi(a, q_lo, q_hi); b = clampi(b, q_lo, q_hi); c = clampi(c, q_lo, q_hi); d = clampi(d, q_lo, q_hi);
-      return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
-    };
-    uint32_t tile_iter = 0;
-    for (int mt = slot; mt < p.m_tiles; mt += p.ctas_per_n, ++tile_iter) {
-      const int n_img = mt / p.tiles_per_img, y0 = (mt - n_img * p.tiles_per_img) * p.R;
-      const uint32_t buf = tile_iter & 1;
-      mbar_wait_small(tfull(buf), (tile_iter >> 1) & 1);
+    int n_img = slot / p.tiles_per_img, ti = slot - n_img * p.tiles_per_img;
+    for (int t = 0; t < my_tiles; ++t) {
+      const uint32_t buf = t & 1;
+      if (ew == 0 && lane == 0) stamp(2, t, 0);
+      mbar_wait_small(tfull(buf), (t >> 1) & 1);
       tc_fence_after();
+      if (ew == 0 && lane == 0) stamp(2, t, 1);
       uint32_t acc[CW];
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + cg * CW;
       if constexpr (CW == 32) tmem_ld32(taddr, acc);
@@ -282,20 +297,38 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(buf));
-      uint32_t w[CW / 4];
+      if (ew == 0 && lane == 0) stamp(2, t, 2);
+      int q[CW];
 #pragma unroll
-      for (int j = 0; j < CW; j += 4) {
-        int q[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double2 cm = cst[j + k];
-          const double d = __hiloint2double(0x43300000, acc[j + k] ^ 0x80000000) - cm.x;
-          q[k] = __double2loint(__fma_rn(d, cm.y, kMagic));
-        }
-        w[j / 4] = pack4_sat(q[0], q[1], q[2], q[3]);
+      for (int j = 0; j < CW; ++j) {
+        const double2 cm = cst[j];
+        const double d = __hiloint2double(0x43300000, acc[j] ^ 0x80000000) - cm.x;
+        q[j] = __double2loint(__fma_rn(d, cm.y, kMagic));
       }
-      if (row_ok && y0 + y < p.H) {
-        uint8_t* g = p.out + ((((size_t)n_img * p.H + y0) * p.W * p.Cout * p.out_bits) >> 3) + row_off;
+      uint32_t w[CW / 4];
+      if (clamp_mode == 1) {              // [0, hi]: unsigned byte saturation, then a per-byte min
+#pragma unroll
+        for (int j = 0; j < CW; j += 4) {
+          uint32_t hi, out;
+          asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(q[j + 3]), "r"(q[j + 2]), "r"(0));
+          asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(q[j + 1]), "r"(q[j]), "r"(hi));
+          w[j / 4] = __vminu4(out, hi4);
+        }
+      } else if (clamp_mode == 2) {       // [-128, 127]: signed byte saturation
+#pragma unroll
+        for (int j = 0; j < CW; j += 4) {
+          uint32_t hi;
+          asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(q[j + 3]), "r"(q[j + 2]), "r"(0));
+          asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w[j / 4]) : "r"(q[j + 1]), "r"(q[j]), "r"(hi));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CW; j += 4)
+          w[j / 4] = __byte_perm(__byte_perm(clampi(q[j], q_lo, q_hi), clampi(q[j + 1], q_lo, q_hi), 0x0040),
+                                 __byte_perm(clampi(q[j + 2], q_lo, q_hi), clampi(q[j + 3], q_lo, q_hi), 0x0040), 0x5410);
+      }
+      if (row_ok && ti * p.R + y < p.H) {
+        uint8_t* g = p.out + (size_t)n_img * img_bytes + (size_t)ti * grp_bytes + row_off;
         if (p.out_bits == 8) {
 #pragma unroll
           for (int j = 0; j < CW / 16; ++j) *reinterpret_cast<uint4*>(g + j * 16) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
@@ -305,6 +338,9 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
             *reinterpret_cast<uint2*>(g + j * 8) = make_uint2(pack_nibbles8(w[4 * j], w[4 * j + 1]), pack_nibbles8(w[4 * j + 2], w[4 * j + 3]));
         }
       }
+      if (ew == 0 && lane == 0) stamp(2, t, 3);
+      n_img += step_n; ti += step_t;
+      if (ti >= p.tiles_per_img) { ti -= p.tiles_per_img; ++n_img; }
     }
     if (bad) atomicOr(p.status, HAWQ_FLAG_BAD_RATIO);
   }

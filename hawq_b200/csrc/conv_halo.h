@@ -9,6 +9,7 @@ namespace hawq {
 int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x, const int8_t* w_ohwi,
                      const hawq_chan* chan, void* out, int32_t* status, void* stream);
 int halo_set_attributes();
+int halo_read_trace(long long* host_out, int n);   // debug timeline of the last conv_halo launch (HAWQ_B200_HALO_TRACE=1)
 const char* halo_last_error();
 
 }  // namespace hawq

@@ -214,6 +214,10 @@ int hawq_retile_weights(hawq_handle* h, const int8_t* w_ohwi, int32_t Cout, int6
  * 1 = conv_halo (3x3 stride-1, A operand read in place), 2 = conv_halo launches that needed the 2-D weight-map fallback;
  * -1 for an unknown family.  Lets tests assert which kernel ran. */
 int64_t hawq_debug_kernel_count(int32_t family);
+/* debug: with HAWQ_B200_HALO_TRACE=1 in the environment every conv_halo launch records clock64 stamps of CTA 0
+ * ([3 roles: producer, MMA issuer, epilogue][64 steps][4 events]); this copies the last launch's buffer to the host (synchronises
+ * the device) and returns the number of int64 values written.  Not for production use. */
+int32_t hawq_debug_halo_trace(int64_t* host_out, int32_t n);
 /* workspace query kept for ABI completeness: this build needs no scratch beyond caller tensors */
 int64_t hawq_workspace_bytes(const hawq_conv_desc* d, const hawq_epilogue_desc* ep);
 

@@ -321,15 +321,89 @@ void run_tma(uint8_t* src, int inner, int rows) {
   cudaFree(d);
 }
 
+// ------------------------------------------------------------------------------------------------ E
+// 4-D boxes with halo (what conv_halo loads): tensor {C bytes, W, H, N}, box {64, W + 2, R + 2, 1} at (0, -1, y0 - 1, n).
+__global__ void __launch_bounds__(64, 1) probe_tma4(const __grid_constant__ CUtensorMap map, int box_bytes, int H, int R, int N, int iters, int nbuf, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t full[8], empty[8];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 8; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&empty[s])));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  __syncthreads();
+  const int stage_bytes = (box_bytes + 1023) / 1024 * 1024;
+  const int tiles_per_img = (H + R - 1) / R;
+  if (threadIdx.x == 0) {
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % nbuf;
+      wait_bar(smem_u32(&empty[s]), ((it / nbuf) & 1) ^ 1);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(box_bytes) : "memory");
+      const int mt = (blockIdx.x + it * gridDim.x) % (tiles_per_img * N);
+      const int n = mt / tiles_per_img, y0 = (mt % tiles_per_img) * R;
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                   ::"r"(smem_u32(smem + s * stage_bytes)), "l"(reinterpret_cast<uint64_t>(&map)), "r"(0), "r"(-1), "r"(y0 - 1), "r"(n), "r"(smem_u32(&full[s])) : "memory");
+    }
+    if (blockIdx.x == 0) out[0] = clock64() - t0;
+  } else if (threadIdx.x == 32) {
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % nbuf;
+      wait_bar(smem_u32(&full[s]), (it / nbuf) & 1);
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+    }
+  }
+  __syncthreads();
+}
+void run_tma4(uint8_t* src, int C, int W, int H, int N, int R, int nbuf, int inner = 64) {
+  static encode_tiled_fn enc = [] {
+    void* ptr = nullptr; cudaDriverEntryPointQueryResult q;
+    cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q);
+    return reinterpret_cast<encode_tiled_fn>(ptr);
+  }();
+  CUtensorMap map;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)C, (cuuint64_t)C * W, (cuuint64_t)C * W * H};
+  const cuuint32_t box[4] = {(cuuint32_t)inner, (cuuint32_t)(W + 2), (cuuint32_t)(R + 2), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  if (!enc || enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("E: encode failed\n"); return; }
+  long long* d; CK(cudaMalloc(&d, 8));
+  const int box_bytes = inner * (W + 2) * (R + 2);
+  const int smem = nbuf * ((box_bytes + 1023) / 1024 * 1024) + 1024;
+  CK(cudaFuncSetAttribute(probe_tma4, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int iters = 2000;
+  probe_tma4<<<148, 64, smem>>>(map, box_bytes, H, R, N, 200, nbuf, d);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  probe_tma4<<<148, 64, smem>>>(map, box_bytes, H, R, N, iters, nbuf, d);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  printf("E: 4-D halo box {%d B, %d, %d, 1} = %5d B over {%d, %d, %d, %d}, %d buffers: %.0f ns per box per SM, %.2f TB/s\n", inner, W + 2, R + 2, box_bytes, C, W, H, N, nbuf,
+         ms * 1e6 / iters, 148.0 * iters * box_bytes / (ms * 1e-3) / 1e12);
+  cudaFree(d);
+}
+
 int main() {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("%s, %d SMs, L2 %d MB\n", prop.name, prop.multiProcessorCount, prop.l2CacheSize >> 20);
   if (getenv("PROBE_DESC")) { run_desc<64>(); run_desc<128>(); run_desc<32>(); }
   uint8_t* src; const size_t cap = 512ull << 20;
   CK(cudaMalloc(&src, cap)); CK(cudaMemset(src, 1, cap));
-  run_tma<1>(src, 64, 128); run_tma<1>(src, 64, 232); run_tma<1>(src, 128, 64); run_tma<1>(src, 128, 116); run_tma<1>(src, 128, 232);
+  if (!getenv("PROBE_E_ONLY")) {
+  run_tma<1>(src, 64, 128); run_tma<1>(src, 64, 232); run_tma<1>(src, 128, 64); run_tma<1>(src, 128, 116);
   run_tma<1>(src, 32, 232); run_tma<1>(src, 64, 32); run_tma<1>(src, 128, 16);
   run_tma<2>(src, 64, 128); run_tma<2>(src, 64, 232); run_tma<4>(src, 64, 128); run_tma<2>(src, 128, 64);
+  }
+  run_tma4(src, 64, 56, 56, 128, 2, 4); run_tma4(src, 64, 56, 56, 128, 2, 8); run_tma4(src, 64, 56, 56, 128, 2, 1);
+  run_tma4(src, 128, 28, 28, 128, 4, 4); run_tma4(src, 128, 28, 28, 128, 4, 4, 128); run_tma4(src, 256, 14, 14, 128, 8, 4); run_tma4(src, 256, 14, 14, 128, 8, 4, 128);
+  run_tma4(src, 64, 56, 56, 128, 0, 4); run_tma4(src, 64, 56, 56, 128, 6, 2);
   if (getenv("PROBE_TMA_ONLY")) return 0;
   for (int chunk : {8192, 16384, 24576}) {
     run_l2<1>(src, 32ull << 20, chunk, 0, "distinct chunks, L2-resident region", 148);
