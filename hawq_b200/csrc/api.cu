@@ -7,6 +7,7 @@
 
 #include <cstdlib>
 
+#include "conv1x1.h"
 #include "conv_halo.h"
 #include "conv_igemm.cuh"
 #include "conv_tc.cuh"
@@ -176,6 +177,7 @@ int hawq_create(int device, hawq_handle** out) {
       (rc = set_tc_attr<TC_EPI_RES44>()) || (rc = set_tc_attr<TC_EPI_RES42>()) || (rc = set_tc_attr<TC_EPI_DUAL>()))
     return rc;
   if ((rc = halo_set_attributes())) return fail(rc, "%s", halo_last_error());
+  if ((rc = c1_set_attributes())) return fail(rc, "%s", c1_last_error());
   CUDA_TRY(cudaFuncSetAttribute(linear_dp4a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, linear_smem_bytes(LIN_MAX_K)));
   if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
       (rc = set_conv_attr<64, true>()))
@@ -315,6 +317,12 @@ int hawq_conv2d(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogue_des
       const int hr = launch_conv_halo(h->sm_count, d, ep, x, w, chan, out, h->status, stream);
       if (hr < 0) return fail(hr, "%s", halo_last_error());
       if (hr == 0 || hr == 2) { ++g_kernel_count[1]; g_kernel_count[2] += hr == 2; return launch_check("conv_halo"); }
+    }
+    // 1x1 stride-1 layers (REQUANT, uint16-stream RESIDUAL): stationary weights, large TMA copies (conv1x1.cuh)
+    if (ep->mode == HAWQ_EPI_REQUANT || ep->mode == HAWQ_EPI_RESIDUAL) {
+      const int cr = launch_conv1x1(h->sm_count, d, ep, x, w, chan, res, out, out_low, h->status, p.sat_pack, stream);
+      if (cr < 0) return fail(cr, "%s", c1_last_error());
+      if (cr == 0) { ++g_kernel_count[3]; return launch_check("conv1x1"); }
     }
     ++g_kernel_count[0];
     const int bn = (d->Cout % 128 == 0) ? 128 : 64;

@@ -54,17 +54,7 @@ __host__ __device__ constexpr int halo_producer_warps(bool a4) { return a4 ? 4 :
 __host__ __device__ constexpr int halo_threads(bool a4) { return (halo_producer_warps(a4) + 1 + HALO_EPI_WARPS) * 32; }   // 576 / 672
 constexpr int HALO_MAX_BUFS = 4;
 
-// TMA: 3-D tiled box global -> shared
-__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
-}
 
-// TMA: 4-D tiled box global -> shared
-__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
-}
 
 template <int BN, bool A4, bool TRACE = false>
 __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap xmap,

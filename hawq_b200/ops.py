@@ -135,11 +135,11 @@ def conv2d(x, desc, ep, w, chan, res=None, res_chan=None, fscale=None, out=None,
     h, s = _ctx(x)
     ev = _begin()
     lib = _lib.load()
-    halo0 = lib.hawq_debug_kernel_count(1) if ev is not None else 0
+    halo0, c10 = (lib.hawq_debug_kernel_count(1), lib.hawq_debug_kernel_count(3)) if ev is not None else (0, 0)
     _lib.check(lib.hawq_conv2d(h, C.byref(desc), C.byref(ep), _p(x), _p(w), _p(chan), _p(res), _p(res_chan),
                                _p(fscale), _p(out), _p(out_low), s))
     if ev is not None:     # per-launch timing (bench.py roofline leg): name the kernel family that took the launch
-        name = "conv_halo" if lib.hawq_debug_kernel_count(1) != halo0 else "conv_tc"
+        name = "conv_halo" if lib.hawq_debug_kernel_count(1) != halo0 else "conv1x1" if lib.hawq_debug_kernel_count(3) != c10 else "conv_tc"
         _count(name, conv_work(desc, ep), ev)
     else:
         _count()

@@ -472,3 +472,59 @@ def test_conv_halo_uses_the_3d_weight_map():
     from hawq_b200 import _lib
     assert _lib.load().hawq_debug_kernel_count(1) > 0 or True
     assert _lib.load().hawq_debug_kernel_count(2) == 0, "cuTensorMapEncodeTiled refused the 3-D weight view: conv_halo ran on the fallback"
+
+
+# ------------------------------------------------------------------------------------------------ conv1x1 (stationary weights)
+C1_GEOMS = [
+    # N, H, W, Cin, Cout
+    (3, 57, 57, 256, 64),      # ResNet-50 stage-1 conv1 shape, 77 ragged row tiles, BN = 64
+    (2, 28, 28, 512, 128),     # KT = 8: two stages of 4 k-tiles per tile
+    (2, 14, 14, 1024, 256),    # KT = 16, two channel blocks
+    (3, 7, 7, 2048, 512),      # KT = 32: BN = 64 (a 128-row weight slab does not fit), 8 channel blocks
+    (5, 20, 20, 64, 256),      # conv3 shape: single k-tile per tile
+    (1, 9, 9, 192, 128),       # KT = 3: KC = 3
+    (40, 30, 30, 128, 512),    # 282 row tiles x 4 channel blocks: several tiles per CTA
+]
+
+
+@pytest.mark.parametrize("a_bits", [8, 4])
+@pytest.mark.parametrize("geom", C1_GEOMS)
+def test_conv1x1_requant_and_residual(geom, a_bits):
+    """1x1 stride-1 layers take the stationary-weights kernel (conv1x1.cuh) for the REQUANT and the uint16-stream RESIDUAL epilogues
+    (ratios <= 1 and the checked <= 2^20 variant): bit-exact vs the ABI model; the launch counter proves which kernel ran."""
+    from hawq_b200 import _lib
+    n, h, w, cin, cout = geom
+    r = rng(sum(v * (i + 11) for i, v in enumerate(geom)) * 8 + a_bits)
+    numel = n * h * w * cout
+    x = rand_act(r, n * h * w * cin, a_bits)
+    wt = torch.from_numpy(r.randint(-128 if a_bits == 8 else -8, 128 if a_bits == 8 else 8, size=(cout, 1, 1, cin)).astype(np.int8))
+    if a_bits == 4:
+        ops.permute_weights_for_i4(wt)
+    d = ops.conv_desc(n, h, w, cin, cout, 1, 1, 1, 0, a_bits)
+    count = lambda: _lib.load().hawq_debug_kernel_count(3)
+    for out_bits, clamp, relu in [(8, (-128, 127), 1), (4, (0, 15), 1), (8, (-128, 127), 0), (8, (-100, 90), 1)]:
+        chan = make_chan(r, cout, ratio_lo=1e-5)
+        ep = ops.epilogue(EPI_REQUANT, relu=relu, out_bits=out_bits, clamp=clamp, flags=TC_FLAG)
+        before = count()
+        (c_out,), (g_out,) = run_both("conv2d", dict(x=x, desc=d, ep=ep, w=wt, chan=chan, out=out_buf(numel, out_bits)), ["out"])
+        assert count() == before + 1, "conv1x1 did not take this REQUANT launch"
+        assert torch.equal(c_out, g_out), (geom, a_bits, out_bits, relu)
+    wt2 = torch.from_numpy(r.randint(-8, 8, size=(cout, 1, 1, cin)).astype(np.int8))
+    if a_bits == 4:
+        ops.permute_weights_for_i4(wt2)
+    for flag, low_bits, ratio_hi, res_ratio in [(1, 8, 0.9, 0.37), (1, 4, 0.9, 0.9), (1, 0, 0.5, 0.11), (2, 8, 40.0, 1.37), (2, 4, 3.0, 2.5)]:
+        chan = make_chan(r, cout, bias_mag=2000, ratio_lo=1e-2, ratio_hi=ratio_hi)
+        res = torch.from_numpy(r.randint(0, 900 if flag == 2 else 40000, size=numel).astype(np.uint16).view(np.int16))
+        ep = ops.epilogue(EPI_RESIDUAL, relu=1, res_kind=0, res_bits=16, res_me=dyadic(res_ratio), y_bits=16, low_bits=low_bits,
+                          low_me=dyadic(0.004 if flag == 1 else 0.0004), low_clamp=(0, 15) if low_bits == 4 else (-128, 127), flags=flag)
+        args = dict(x=x, desc=d, ep=ep, w=wt2, chan=chan, res=res, out=out_buf(numel, 16), out_low=out_buf(numel, low_bits) if low_bits else None)
+        keys = [k_ for k_ in ("out", "out_low") if args[k_] is not None]
+        ops.reset_status(0)
+        before = count()
+        cs, gs = run_both("conv2d", args, keys)
+        fits = not (a_bits == 4 and cin >= 2048)      # packed stages + residual tiles + a 128 KB weight slab exceed shared memory
+        assert count() == before + (1 if fits else 0), "conv1x1 did not take this RESIDUAL launch"
+        assert ops.get_status(0) & 6 == 0
+        for a, b, k_ in zip(cs, gs, keys):
+            assert torch.equal(a, b), (geom, a_bits, flag, low_bits, k_)
+    ops.reset_status(0)

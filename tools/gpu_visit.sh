@@ -9,6 +9,9 @@ for what in "$@"; do
     probe)
       nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/probe_b200 tools/probe_b200.cu && PROBE_TMA_ONLY=${PROBE_TMA_ONLY:-} timeout 200 /tmp/probe_b200 > gpurun_out/probe_b200.txt 2>&1
       echo "probe exit $?"; tail -30 gpurun_out/probe_b200.txt;;
+    c1)
+      timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "conv1x1" > gpurun_out/pytest_c1.log 2>&1
+      echo "c1 exit $?"; tail -15 gpurun_out/pytest_c1.log;;
     halo)
       timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "halo" > gpurun_out/pytest_halo.log 2>&1
       echo "halo exit $?"; tail -15 gpurun_out/pytest_halo.log;;
