@@ -39,28 +39,35 @@ struct C1Plan {
   C1Params p;
 };
 
+// shared-memory carve-up; prefers deep activation stages (fewer TMA operations), then more of them
 static bool plan_for(int bn, bool a4, bool res, int KT, C1Plan* out) {
   C1Params& p = out->p;
-  p.KC = largest_divisor_le(KT, 4);
   const int w_bytes = KT * bn * 64;
-  const int a_stage = p.KC * 128 * 64;
-  const int k_stage = a4 ? p.KC * 128 * 32 : 0;
   const int res_bytes = res ? 2 * 128 * bn * 2 : 0;
+  const int y_bytes = res ? 128 * bn * 2 : 0;      // staged uint16 output tile
+  const int low_bytes = 128 * bn;                   // staged 8 / 4-bit output tile (REQUANT output, RESIDUAL low-bit copy)
   const int cst = bn * 16, bars = 256;
-  for (int ns = C1_MAX_STAGES; ns >= 2; --ns) {
-    int off = round_up(w_bytes, 1024);
-    p.off_a = off; off += ns * a_stage;
-    p.off_packed = off; off += ns * k_stage;
-    off = round_up(off, 1024);
-    p.off_res = off; off += res_bytes;
-    p.off_cst = off; off += cst;
-    p.off_bar = off; off += bars;
-    const int total = off + 1024;
-    if (total <= C1_SMEM_MAX) {
-      out->bn = bn; out->total = total; p.NS = ns;
-      p.w_box_kt = largest_divisor_le(KT, bn == 128 ? 8 : 16);
-      p.w_boxes = KT / p.w_box_kt;
-      return true;
+  for (int kc = 4; kc >= 1; --kc) {
+    if (KT % kc) continue;
+    const int a_stage = kc * 128 * 64;
+    const int k_stage = a4 ? kc * 128 * 32 : 0;
+    for (int ns = (kc == 4 ? 3 : C1_MAX_STAGES); ns >= 2; --ns) {
+      int off = round_up(w_bytes, 1024);
+      p.off_a = off; off += ns * a_stage;
+      p.off_packed = off; off += ns * k_stage;
+      off = round_up(off, 1024);
+      p.off_res = off; off += res_bytes;
+      p.off_y = off; off += y_bytes;
+      p.off_low = off; off += low_bytes;
+      p.off_cst = off; off += cst;
+      p.off_bar = off; off += bars;
+      const int total = off + 1024;
+      if (total <= C1_SMEM_MAX) {
+        out->bn = bn; out->total = total; p.NS = ns; p.KC = kc;
+        p.w_box_kt = largest_divisor_le(KT, bn == 128 ? 8 : 16);
+        p.w_boxes = KT / p.w_box_kt;
+        return true;
+      }
     }
   }
   return false;
@@ -170,9 +177,26 @@ int launch_conv1x1(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_de
     const cuuint64_t dims[3] = {128, (cuuint64_t)M, (cuuint64_t)d->Cout * 2 / 128};
     const cuuint64_t strides[2] = {(cuuint64_t)d->Cout * 2, 128};
     const cuuint32_t box[3] = {128u, 128u, (cuuint32_t)(plan.bn / 64)};
-    const CUresult r = enc(&maps.res, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(res), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { snprintf(g_c1_err, sizeof(g_c1_err), "conv1x1: cuTensorMapEncodeTiled (residual) failed (%d)", (int)r); return HAWQ_ERR_CUDA; }
+    CUresult r = enc(&maps.res, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(res), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+      r = enc(&maps.y, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(g_c1_err, sizeof(g_c1_err), "conv1x1: cuTensorMapEncodeTiled (residual stream) failed (%d)", (int)r); return HAWQ_ERR_CUDA; }
+  }
+  {   // 8 / 4-bit output tile: REQUANT output, or the low-bit copy of the RESIDUAL epilogue
+    const int bits = is_res ? ep->low_bits : ep->out_bits;
+    void* base = is_res ? out_low : out;
+    if (bits) {
+      const cuuint32_t rb = (cuuint32_t)(plan.bn * bits / 8);        // 128 / 64 / 32
+      const cuuint64_t dims[2] = {(cuuint64_t)d->Cout * bits / 8, (cuuint64_t)M};
+      const cuuint64_t strides[1] = {(cuuint64_t)d->Cout * bits / 8};
+      const cuuint32_t box[2] = {rb, 128u};
+      const CUresult r = enc(&maps.low, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { snprintf(g_c1_err, sizeof(g_c1_err), "conv1x1: cuTensorMapEncodeTiled (low-bit output) failed (%d)", (int)r); return HAWQ_ERR_CUDA; }
+    }
   }
   const int grid = p.n_tiles * p.ctas_per_n;
   cudaStream_t st = (cudaStream_t)stream;

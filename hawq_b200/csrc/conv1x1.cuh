@@ -7,8 +7,9 @@
 //     straight from the OHWI / [Cout][K] matrix) and the CTA walks over row tiles;
 //   * activations arrive as ONE 3-D TMA box per stage: {64 B, 128 rows, KC k-tiles} -> [k-tile][128][64 B] SWIZZLE_64B blocks
 //     (up to 32 KB per copy) instead of one 8 KB copy per k-tile;
-//   * the uint16 residual tile of the case-1 epilogue is one box {128 B, 128 rows, BN / 64} per tile (was 8), outputs are
-//     written by the threads themselves (every thread owns one row and 16 / 32 consecutive channels: full 32-byte sectors);
+//   * the uint16 residual tile of the case-1 epilogue is one box {128 B, 128 rows, BN / 64} per tile (was 8); outputs are staged
+//     in shared memory (swizzled tiles) and leave with ONE TMA store per tile and output tensor (rows written by the threads
+//     themselves - 16 to 64 B per row and thread - ran the store path at a fraction of its rate: profiles/r02);
 //   * one elected lane issues the MMAs with descriptors advanced by constants (one add each);
 //   * 16 epilogue warps (four per TMEM lane quarter), accumulator released to the MMA warp right after tcgen05.ld.
 // Epilogues: REQUANT -> int8 / packed uint4 (QuantAct case 0, quant_utils.py:390-413) and RESIDUAL uint16-in / uint16-out with the
@@ -34,7 +35,7 @@ struct C1Params {
   uint32_t res_m; int res_e;                                   // RESIDUAL: scalar ratio of the uint16 stream
   int low_bits; uint32_t low_m; int low_e, low_lo, low_hi;     // RESIDUAL: low-bit copy
   int sat_pack;
-  int off_a, off_packed, off_res, off_cst, off_bar;            // shared-memory carve-up (weights at 0)
+  int off_a, off_packed, off_res, off_y, off_low, off_cst, off_bar;   // shared-memory carve-up (weights at 0)
 };
 
 constexpr int C1_EPI_WARPS = 16;
@@ -47,6 +48,8 @@ struct alignas(64) C1Maps {
   CUtensorMap a;     // activations {64 | 32 B, M rows (pitch K bytes), KT}: box {64 | 32, 128, KC}
   CUtensorMap w;     // weights     {64 B, Cout rows (pitch K), KT}:        box {64, BN, w_box_kt}
   CUtensorMap res;   // uint16 stream {128 B, M rows (pitch 2 Cout), 2 Cout / 128}: box {128, 128, BN / 64}, SWIZZLE_128B
+  CUtensorMap y;     // uint16 stream out, same geometry
+  CUtensorMap low;   // 8 / 4-bit output [M][Cout * bits / 8]: box {BN * bits / 8, 128}, swizzle by row length
 };
 
 template <int BN, int EPI, bool WIDE, bool A4>
@@ -242,16 +245,15 @@ __global__ void __launch_bounds__(c1_threads(A4), 1) conv1x1_kernel(const C1Para
     asm volatile("bar.sync 1, %0;" ::"n"(C1_EPI_WARPS * 32));
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int row = quarter * 32 + lane;
-    const int c0 = n0 + cg * CW;
     const double2* cst = sCst + cg * CW;
 
+    const bool elect_x = (ew == 0 && lane == 0);     // issues the TMA stores of the epilogue
     if constexpr (EPI == C1_REQ) {
       const int q_lo = p.relu ? max(p.lo, 0) : p.lo, q_hi = p.hi;
       const int clamp_mode = (q_lo == 0 && q_hi >= 0 && q_hi <= 255) ? 1 : (q_lo == -128 && q_hi == 127) ? 2 : 0;
       const uint32_t hi4 = (uint32_t)(q_hi & 0xFF) * 0x01010101u;
       for (int t = 0; t < my_tiles; ++t) {
         const uint32_t buf = t & 1;
-        const int m = (slot + t * p.ctas_per_n) * 128 + row;
         mbar_wait_small(tfull(buf), (t >> 1) & 1);
         tc_fence_after();
         uint32_t acc[CW];
@@ -291,18 +293,31 @@ __global__ void __launch_bounds__(c1_threads(A4), 1) conv1x1_kernel(const C1Para
             w[j / 4] = __byte_perm(__byte_perm(clampi(q[j], q_lo, q_hi), clampi(q[j + 1], q_lo, q_hi), 0x0040),
                                    __byte_perm(clampi(q[j + 2], q_lo, q_hi), clampi(q[j + 3], q_lo, q_hi), 0x0040), 0x5410);
         }
-        if (m < p.M) {
-          uint8_t* g = p.out + ((((size_t)m * p.Cout + c0) * p.out_bits) >> 3);
-          if (p.out_bits == 8) {
+        // stage this thread's CW * bits / 8 bytes in the swizzled output tile; one TMA store per tile (rows >= M are clipped)
+        const int rb_out = BN * p.out_bits / 8;                  // tile row bytes: 128 / 64 / 32
+        if (elect_x) bulk_wait_read_all();                        // the previous tile's store has finished reading the staging tile
+        asm volatile("bar.sync 1, %0;" ::"n"(C1_EPI_WARPS * 32));
+        uint8_t* lt = smem + p.off_low;
+        if (p.out_bits == 8) {
 #pragma unroll
-            for (int j = 0; j < CW / 16; ++j) *reinterpret_cast<uint4*>(g + j * 16) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-          } else {            // hawq nibble order: per 8 channels, byte j = c_j | c_{j+4} << 4
+          for (int j = 0; j < CW / 16; ++j)
+            *reinterpret_cast<uint4*>(lt + tile_piece_off(rb_out, row, cg * (CW / 16) + j)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        } else {            // hawq nibble order: per 8 channels, byte j = c_j | c_{j+4} << 4
 #pragma unroll
-            for (int j = 0; j < CW / 16; ++j)
-              *reinterpret_cast<uint2*>(g + j * 8) = make_uint2(pack_nibbles8(w[4 * j], w[4 * j + 1]), pack_nibbles8(w[4 * j + 2], w[4 * j + 3]));
+          for (int j = 0; j < CW / 16; ++j) {
+            const int boff = cg * (CW / 2) + j * 8;             // byte offset of these 16 channels in the row
+            *reinterpret_cast<uint2*>(lt + tile_piece_off(rb_out, row, boff >> 4) + (boff & 8)) =
+                make_uint2(pack_nibbles8(w[4 * j], w[4 * j + 1]), pack_nibbles8(w[4 * j + 2], w[4 * j + 3]));
           }
         }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(C1_EPI_WARPS * 32));
+        if (elect_x) {
+          tma_store_2d(&maps.low, n0 * p.out_bits / 8, (slot + t * p.ctas_per_n) * 128, smem_base + p.off_low);
+          bulk_commit();
+        }
       }
+      if (elect_x) bulk_wait_all();
     } else {
       // ---- case 1: y = max(RHE((acc + bias) * M_c) + RHE(res * res_M), 0) -> uint16 stream (sticky overflow flag), plus
       //      low = clamp(RHE(y * low_M)) for the next unit; unsigned operands use the folded one-FMA form (exact for e <= 51)
@@ -317,7 +332,6 @@ __global__ void __launch_bounds__(c1_threads(A4), 1) conv1x1_kernel(const C1Para
       const uint32_t r_chunk = (uint32_t)(cg * CW) / 64, r_piece0 = ((uint32_t)(cg * CW) % 64) / 8;
       for (int t = 0; t < my_tiles; ++t) {
         const uint32_t buf = t & 1;
-        const int m = (slot + t * p.ctas_per_n) * 128 + row;
         mbar_wait_small(rfull(buf), (t >> 1) & 1);
         const uint8_t* rrow = smem + p.off_res + buf * RES_BYTES + r_chunk * (128 * 128) + row * 128;
         uint4 rv[CW / 8];
@@ -335,9 +349,8 @@ __global__ void __launch_bounds__(c1_threads(A4), 1) conv1x1_kernel(const C1Para
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(buf));
-        const bool row_ok = m < p.M;
-        uint8_t* gy = p.out + ((size_t)m * p.Cout + c0) * 2;
-        uint8_t* gl = p.out_low + ((((size_t)m * p.Cout + c0) * p.low_bits) >> 3);
+        uint4 yo[CW / 8];
+        uint32_t lw[CW / 4];
 #pragma unroll
         for (int i = 0; i < CW / 8; ++i) {           // groups of 8 channels: one 16-byte vector of residuals, one of outputs
           const uint32_t rr[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
@@ -360,38 +373,63 @@ __global__ void __launch_bounds__(c1_threads(A4), 1) conv1x1_kernel(const C1Para
             y[k] = max(sum, 0);
             ymax = max(ymax, y[k]);
           }
-          uint4 o;
-          asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(o.x) : "r"(y[1]), "r"(y[0]));
-          asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(o.y) : "r"(y[3]), "r"(y[2]));
-          asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(o.z) : "r"(y[5]), "r"(y[4]));
-          asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(o.w) : "r"(y[7]), "r"(y[6]));
-          if (row_ok) *reinterpret_cast<uint4*>(gy + i * 16) = o;
+          asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(yo[i].x) : "r"(y[1]), "r"(y[0]));
+          asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(yo[i].y) : "r"(y[3]), "r"(y[2]));
+          asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(yo[i].z) : "r"(y[5]), "r"(y[4]));
+          asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(yo[i].w) : "r"(y[7]), "r"(y[6]));
           if (p.low_bits) {
             int q[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) q[k] = __double2loint(__fma_rn(__hiloint2double(0x43300000, y[k]), low_M, low_C));   // y >= 0
-            uint32_t w0, w1;
             if (sat8) {
               uint32_t h0, h1;
               asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(h0) : "r"(q[3]), "r"(q[2]), "r"(0));
-              asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w0) : "r"(q[1]), "r"(q[0]), "r"(h0));
+              asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(lw[2 * i]) : "r"(q[1]), "r"(q[0]), "r"(h0));
               asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(h1) : "r"(q[7]), "r"(q[6]), "r"(0));
-              asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w1) : "r"(q[5]), "r"(q[4]), "r"(h1));
+              asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(lw[2 * i + 1]) : "r"(q[5]), "r"(q[4]), "r"(h1));
             } else {
 #pragma unroll
               for (int k = 0; k < 8; ++k) q[k] = clampi(q[k], l_lo, l_hi);
-              w0 = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
-              w1 = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
-            }
-            if (row_ok) {
-              if (p.low_bits == 8) *reinterpret_cast<uint2*>(gl + i * 8) = make_uint2(w0, w1);
-              else *reinterpret_cast<uint32_t*>(gl + i * 4) = pack_nibbles8(w0, w1);
+              lw[2 * i] = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+              lw[2 * i + 1] = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
             }
           }
         }
+        // the residual values were consumed: hand the buffer back (an arrive issued right behind the loads can overtake them)
         __syncwarp();
         if (lane == 0) mbar_arrive(rempty(buf));
+        // stage y ([64-column chunk][128 rows][128 B], SWIZZLE_128B) and the low-bit tile; one TMA store each per tile
+        if (elect_x) bulk_wait_read_all();                        // the previous tile's stores have finished reading the staging tiles
+        asm volatile("bar.sync 1, %0;" ::"n"(C1_EPI_WARPS * 32));
+        uint8_t* yt = smem + p.off_y + r_chunk * (128 * 128);
+#pragma unroll
+        for (int i = 0; i < CW / 8; ++i) *reinterpret_cast<uint4*>(yt + tile_piece_off(128, row, (int)r_piece0 + i)) = yo[i];
+        if (p.low_bits) {
+          uint8_t* lt = smem + p.off_low;
+          const int rb_low = BN * p.low_bits / 8;                 // 128 / 64 / 32
+          if (p.low_bits == 8) {
+#pragma unroll
+            for (int j = 0; j < CW / 16; ++j)
+              *reinterpret_cast<uint4*>(lt + tile_piece_off(rb_low, row, cg * (CW / 16) + j)) = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW / 16; ++j) {
+              const int boff = cg * (CW / 2) + j * 8;
+              *reinterpret_cast<uint2*>(lt + tile_piece_off(rb_low, row, boff >> 4) + (boff & 8)) =
+                  make_uint2(pack_nibbles8(lw[4 * j], lw[4 * j + 1]), pack_nibbles8(lw[4 * j + 2], lw[4 * j + 3]));
+            }
+          }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(C1_EPI_WARPS * 32));
+        if (elect_x) {
+          const int m0 = (slot + t * p.ctas_per_n) * 128;
+          tma_store_3d(&maps.y, 0, m0, n0 / 64, smem_base + p.off_y);
+          if (p.low_bits) tma_store_2d(&maps.low, n0 * p.low_bits / 8, m0, smem_base + p.off_low);
+          bulk_commit();
+        }
       }
+      if (elect_x) bulk_wait_all();
       if (ymax > 65535) atomicOr(p.status, HAWQ_FLAG_RESIDUAL_OVERFLOW);
     }
     if (bad) atomicOr(p.status, HAWQ_FLAG_BAD_RATIO);

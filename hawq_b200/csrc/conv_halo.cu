@@ -48,6 +48,7 @@ static bool plan_for(int bn, bool a4, int K, int wp, int R, HaloPlan* out) {
   const int b_bytes = (K / 64) * bn * 64;
   const int patch_alloc = round_up((128 + 2 * wp + 2) * 64, 1024);
   const int packed_alloc = a4 ? round_up((R + 2) * wp * 32, 1024) : 0;
+  const int out_tile = 128 * bn;       // staged output tile (8-bit worst case)
   const int cst = bn * 16;
   const int bars = 256;
   for (int npb = a4 ? 2 : HALO_MAX_BUFS; npb >= 2; --npb) {
@@ -56,6 +57,8 @@ static bool plan_for(int bn, bool a4, int K, int wp, int R, HaloPlan* out) {
     HaloParams& p = out->p;
     p.off_patch = off; off += npb * patch_alloc;
     p.off_packed = off; off += nkb * packed_alloc;
+    off = round_up(off, 1024);
+    p.off_out = off; off += out_tile;
     p.off_cst = off; off += cst;
     p.off_bar = off; off += bars;
     const int total = off + 1024;      // slack for the 1024-byte alignment of the base
@@ -85,7 +88,7 @@ int halo_set_attributes() {
 }
 
 template <int BN, bool A4>
-static void launch(const HaloPlan& plan, const CUtensorMap& map, const CUtensorMap& wmap, int grid, cudaStream_t st) {
+static void launch(const HaloPlan& plan, const CUtensorMap& map, const CUtensorMap& wmap, const CUtensorMap& omap, int grid, cudaStream_t st) {
   static const bool pdl = [] { const char* e = getenv("HAWQ_B200_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -98,8 +101,8 @@ static void launch(const HaloPlan& plan, const CUtensorMap& map, const CUtensorM
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  if (plan.p.trace) cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, A4, true>, plan.p, map, wmap);
-  else cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, A4, false>, plan.p, map, wmap);
+  if (plan.p.trace) cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, A4, true>, plan.p, map, wmap, omap);
+  else cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, A4, false>, plan.p, map, wmap, omap);
 }
 
 int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x, const int8_t* w_ohwi,
@@ -165,10 +168,23 @@ int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_
     p.w_rank3 = 0;
   }
 
+  // output [N][H][W][Cout * bits / 8] as {bytes, W, H, N}: store box {BN * bits / 8, W + 2, R, 1} (x >= W and y >= H are clipped)
+  CUtensorMap omap;
+  {
+    const cuuint64_t ob = (cuuint64_t)d->Cout * ep->out_bits / 8;
+    const cuuint32_t rb = (cuuint32_t)(plan.bn * ep->out_bits / 8);
+    const cuuint64_t odims[4] = {ob, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    const cuuint64_t ostrides[3] = {ob, ob * d->W, ob * d->W * d->H};
+    const cuuint32_t obox[4] = {rb, (cuuint32_t)wp, (cuuint32_t)R, 1u};
+    const CUresult ro = enc(&omap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, out, odims, ostrides, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (ro != CUDA_SUCCESS) { snprintf(g_halo_err, sizeof(g_halo_err), "conv_halo: cuTensorMapEncodeTiled (output) failed (%d)", (int)ro); return HAWQ_ERR_CUDA; }
+  }
   const int grid = p.n_tiles * p.ctas_per_n;
   cudaStream_t st = (cudaStream_t)stream;
-  if (plan.bn == 128) { if (a4) launch<128, true>(plan, map, wmap, grid, st); else launch<128, false>(plan, map, wmap, grid, st); }
-  else { if (a4) launch<64, true>(plan, map, wmap, grid, st); else launch<64, false>(plan, map, wmap, grid, st); }
+  if (plan.bn == 128) { if (a4) launch<128, true>(plan, map, wmap, omap, grid, st); else launch<128, false>(plan, map, wmap, omap, grid, st); }
+  else { if (a4) launch<64, true>(plan, map, wmap, omap, grid, st); else launch<64, false>(plan, map, wmap, omap, grid, st); }
   return p.w_rank3 ? 0 : 2;
 }
 

@@ -46,7 +46,7 @@ struct HaloParams {
   int relu, out_bits, lo, hi;
   long long* trace;          // debug timeline (hawq_debug_halo_trace): [3 roles][64][4] clock64 stamps of CTA 0, or null
   int w_rank3;               // weights tensor map: 1 = {Cin, Cout, 9 taps} 3-D view, 0 = plain [Cout][K] matrix
-  int off_patch, off_packed, off_cst, off_bar;   // shared-memory carve-up (bytes from the 1024-aligned base; weights at 0)
+  int off_patch, off_packed, off_out, off_cst, off_bar;   // shared-memory carve-up (bytes from the 1024-aligned base; weights at 0)
 };
 
 constexpr int HALO_EPI_WARPS = 16;
@@ -58,7 +58,7 @@ constexpr int HALO_MAX_BUFS = 4;
 
 template <int BN, bool A4, bool TRACE = false>
 __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const HaloParams p, const __grid_constant__ CUtensorMap xmap,
-                                                                        const __grid_constant__ CUtensorMap wmap) {
+                                                                        const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap omap) {
   constexpr int B_STAGE = BN * 64;
   constexpr int NPW = halo_producer_warps(A4);   // producer (+ converter) warps
   constexpr int MMA_WARP = NPW;
@@ -264,13 +264,8 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
     asm volatile("griddepcontrol.wait;" ::: "memory");
     // this thread's output position is the same in every tile: position pos = TMEM lane, (y, x) inside the row group
     const int pos = quarter * 32 + lane;
-    const int y = pos / p.wp, x = pos - y * p.wp;
-    const bool row_ok = pos < p.R * p.wp && x < p.W;
-    const int c0 = n0 + cg * CW;
-    // output address of this thread's row: tile base (image, first row of the group) + a per-thread constant
-    const size_t row_off = (((size_t)y * p.W + x) * p.Cout + c0) * p.out_bits >> 3;
-    const size_t img_bytes = ((size_t)p.H * p.W * p.Cout * p.out_bits) >> 3, grp_bytes = ((size_t)p.R * p.W * p.Cout * p.out_bits) >> 3;
     const double2* cst = sCst + cg * CW;
+    const bool elect_x = (ew == 0 && lane == 0);     // issues the TMA stores
     int n_img = slot / p.tiles_per_img, ti = slot - n_img * p.tiles_per_img;
     for (int t = 0; t < my_tiles; ++t) {
       const uint32_t buf = t & 1;
@@ -317,21 +312,36 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
           w[j / 4] = __byte_perm(__byte_perm(clampi(q[j], q_lo, q_hi), clampi(q[j + 1], q_lo, q_hi), 0x0040),
                                  __byte_perm(clampi(q[j + 2], q_lo, q_hi), clampi(q[j + 3], q_lo, q_hi), 0x0040), 0x5410);
       }
-      if (row_ok && ti * p.R + y < p.H) {
-        uint8_t* g = p.out + (size_t)n_img * img_bytes + (size_t)ti * grp_bytes + row_off;
-        if (p.out_bits == 8) {
+      // stage the tile ([position][BN * bits / 8 bytes], swizzled by row length) and store it with ONE 4-D TMA box
+      // {row bytes, W + 2, R, 1} at (channel block, 0, first row, image): the waste columns x >= W and rows past the image are
+      // out of bounds of the output tensor and are clipped by the TMA unit
+      const int rb_out = BN * p.out_bits / 8;                  // 128 / 64 / 32
+      if (elect_x) bulk_wait_read_all();                        // the previous tile's store has finished reading the staging tile
+      asm volatile("bar.sync 1, %0;" ::"n"(HALO_EPI_WARPS * 32));
+      uint8_t* lt = smem + p.off_out;
+      if (p.out_bits == 8) {
 #pragma unroll
-          for (int j = 0; j < CW / 16; ++j) *reinterpret_cast<uint4*>(g + j * 16) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-        } else {            // hawq nibble order: per 8 channels, byte j = c_j | c_{j+4} << 4
+        for (int j = 0; j < CW / 16; ++j)
+          *reinterpret_cast<uint4*>(lt + tile_piece_off(rb_out, pos, cg * (CW / 16) + j)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      } else {            // hawq nibble order: per 8 channels, byte j = c_j | c_{j+4} << 4
 #pragma unroll
-          for (int j = 0; j < CW / 16; ++j)
-            *reinterpret_cast<uint2*>(g + j * 8) = make_uint2(pack_nibbles8(w[4 * j], w[4 * j + 1]), pack_nibbles8(w[4 * j + 2], w[4 * j + 3]));
+        for (int j = 0; j < CW / 16; ++j) {
+          const int boff = cg * (CW / 2) + j * 8;
+          *reinterpret_cast<uint2*>(lt + tile_piece_off(rb_out, pos, boff >> 4) + (boff & 8)) =
+              make_uint2(pack_nibbles8(w[4 * j], w[4 * j + 1]), pack_nibbles8(w[4 * j + 2], w[4 * j + 3]));
         }
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, %0;" ::"n"(HALO_EPI_WARPS * 32));
+      if (elect_x) {
+        tma_store_4d(&omap, n0 * p.out_bits / 8, 0, ti * p.R, n_img, smem_base + p.off_out);
+        bulk_commit();
       }
       if (ew == 0 && lane == 0) stamp(2, t, 3);
       n_img += step_n; ti += step_t;
       if (ti >= p.tiles_per_img) { ti -= p.tiles_per_img; ++n_img; }
     }
+    if (elect_x) bulk_wait_all();
     if (bad) atomicOr(p.status, HAWQ_FLAG_BAD_RATIO);
   }
 

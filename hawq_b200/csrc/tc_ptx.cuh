@@ -70,6 +70,20 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_src) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, uint32_t smem_src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_src) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t smem_src) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_src) : "memory");
+}
+// byte offset of the 16-byte piece `piece` of row `row` in a dense tile of `row_bytes`-byte rows written / read by TMA with the
+// swizzle mode matching the row length (128 / 64 / 32 / 16 B rows -> SWIZZLE_128B / 64B / 32B / NONE), tile base 1024-aligned
+__device__ __forceinline__ uint32_t tile_piece_off(int row_bytes, int row, int piece) {
+  const int x = row_bytes == 128 ? (row & 7) : row_bytes == 64 ? ((row >> 1) & 3) : row_bytes == 32 ? ((row >> 2) & 1) : 0;
+  return (uint32_t)(row * row_bytes + ((piece ^ x) << 4));
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
