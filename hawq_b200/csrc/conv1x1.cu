@@ -97,7 +97,7 @@ static void launch(const C1Plan& plan, const C1Maps& maps, int grid, cudaStream_
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(c1_threads(A4), 1, 1);
+  cfg.blockDim = dim3(c1_threads(A4, EPI), 1, 1);
   cfg.dynamicSmemBytes = (size_t)plan.total;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

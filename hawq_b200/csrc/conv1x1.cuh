@@ -42,7 +42,8 @@ constexpr int C1_EPI_WARPS = 16;
 constexpr int C1_MAX_STAGES = 4;
 constexpr int C1_REQ = 0, C1_RES = 1;
 __host__ __device__ constexpr int c1_producer_warps(bool a4) { return a4 ? 4 : 1; }
-__host__ __device__ constexpr int c1_threads(bool a4) { return (c1_producer_warps(a4) + 1 + C1_EPI_WARPS) * 32; }
+// warps: producers (1, or 4 converters for packed input) | MMA issuer | residual loader (RESIDUAL epilogue only) | 16 epilogue warps
+__host__ __device__ constexpr int c1_threads(bool a4, int epi) { return (c1_producer_warps(a4) + 1 + (epi == C1_RES ? 1 : 0) + C1_EPI_WARPS) * 32; }
 
 struct alignas(64) C1Maps {
   CUtensorMap a;     // activations {64 | 32 B, M rows (pitch K bytes), KT}: box {64 | 32, 128, KC}
@@ -53,11 +54,11 @@ struct alignas(64) C1Maps {
 };
 
 template <int BN, int EPI, bool WIDE, bool A4>
-__global__ void __launch_bounds__(c1_threads(A4), 1) conv1x1_kernel(const C1Params p, const __grid_constant__ C1Maps maps) {
+__global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C1Params p, const __grid_constant__ C1Maps maps) {
   constexpr int B_STAGE = BN * 64;           // one weight k-tile
   constexpr int A_TILE = 128 * 64;           // one activation k-tile (int8)
   constexpr int NPW = c1_producer_warps(A4);
-  constexpr int MMA_WARP = NPW, EPI_WARP0 = NPW + 1;
+  constexpr int MMA_WARP = NPW, RES_WARP = NPW + 1, EPI_WARP0 = NPW + 1 + (EPI == C1_RES ? 1 : 0);
   constexpr int CW = BN / 4;                 // columns per epilogue warp: 16 / 32
   constexpr int TMEM_COLS = 2 * BN;
   constexpr int RES_BYTES = 128 * BN * 2;    // residual tile (uint16)
@@ -119,15 +120,9 @@ __global__ void __launch_bounds__(c1_threads(A4), 1) conv1x1_kernel(const C1Para
     const uint32_t stage_bytes = (uint32_t)p.KC * (A4 ? A_TILE / 2 : A_TILE);
     if constexpr (!A4) {
       if (warp == 0 && elect_one()) {
-        uint32_t s = 0, ph = 0, rb = 0, rph = 0;
+        uint32_t s = 0, ph = 0;
         for (int t = 0; t < my_tiles; ++t) {
           const int m0 = (slot + t * p.ctas_per_n) * 128;
-          if constexpr (EPI == C1_RES) {       // this tile's residual rows (epilogue operand), one box
-            mbar_wait_small(rempty(rb), rph ^ 1);
-            mbar_arrive_expect_tx(rfull(rb), RES_BYTES);
-            tma_load_3d(smem_base + p.off_res + rb * RES_BYTES, &maps.res, 0, m0, n0 / 64, rfull(rb));
-            if (++rb == 2) { rb = 0; rph ^= 1; }
-          }
           for (int k0 = 0; k0 < p.KT; k0 += p.KC) {
             mbar_wait_small(aempty(s), ph ^ 1);
             mbar_arrive_expect_tx(afull(s), stage_bytes);
@@ -158,19 +153,6 @@ __global__ void __launch_bounds__(c1_threads(A4), 1) conv1x1_kernel(const C1Para
           if (g + p.NS - 1 < total_g && elect_one()) issue(g + p.NS - 1);
           __syncwarp();
         }
-        if constexpr (EPI == C1_RES) {
-          // residual rows of the tile whose first stage is being converted: issued by a lane of warp 1 with no look-ahead (waiting
-          // for the buffer depends only on tiles whose stages were converted long ago, so this cannot deadlock the converters)
-          if (warp == 1 && g % stages_per_tile == 0) {
-            if (elect_one()) {
-              const int t = g / stages_per_tile, rb = t & 1;
-              mbar_wait_small(rempty(rb), ((t >> 1) & 1) ^ 1);
-              mbar_arrive_expect_tx(rfull(rb), RES_BYTES);
-              tma_load_3d(smem_base + p.off_res + rb * RES_BYTES, &maps.res, 0, (slot + t * p.ctas_per_n) * 128, n0 / 64, rfull(rb));
-            }
-            __syncwarp();
-          }
-        }
         const int s = g % p.NS;
         mbar_wait_small(kfull(s), (g / p.NS) & 1);
         mbar_wait_small(aempty(s), ((g / p.NS) & 1) ^ 1);
@@ -178,19 +160,42 @@ __global__ void __launch_bounds__(c1_threads(A4), 1) conv1x1_kernel(const C1Para
         uint8_t* dst = smem + p.off_a + s * (p.KC * A_TILE);
         const int r = tid;                                      // one row per thread, every k-tile of the stage
         const uint32_t p_sw = (r >> 2) & 1, a_sw = (r >> 1) & 3;
-        for (int kt = 0; kt < p.KC; ++kt) {
+        // all loads of the stage first (KC <= 4 k-tiles x 2 vectors in flight), then the expansion: this warp is alone on its
+        // scheduler, so instruction-level parallelism is what hides the shared-memory latency
+        uint4 wv[4][2];
 #pragma unroll
-          for (int blk = 0; blk < 2; ++blk) {
-            const uint4 wv = *reinterpret_cast<const uint4*>(src + kt * (A_TILE / 2) + r * 32 + ((blk ^ p_sw) << 4));
-            const uint4 lo = make_uint4(wv.x & 0x0F0F0F0Fu, wv.y & 0x0F0F0F0Fu, wv.z & 0x0F0F0F0Fu, wv.w & 0x0F0F0F0Fu);
-            const uint4 hi = make_uint4((wv.x >> 4) & 0x0F0F0F0Fu, (wv.y >> 4) & 0x0F0F0F0Fu, (wv.z >> 4) & 0x0F0F0F0Fu, (wv.w >> 4) & 0x0F0F0F0Fu);
-            *reinterpret_cast<uint4*>(dst + kt * A_TILE + r * 64 + (((2 * blk) ^ a_sw) << 4)) = lo;
-            *reinterpret_cast<uint4*>(dst + kt * A_TILE + r * 64 + (((2 * blk + 1) ^ a_sw) << 4)) = hi;
+        for (int kt = 0; kt < 4; ++kt)
+          if (kt < p.KC) {
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) wv[kt][blk] = *reinterpret_cast<const uint4*>(src + kt * (A_TILE / 2) + r * 32 + ((blk ^ p_sw) << 4));
           }
-        }
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt)
+          if (kt < p.KC) {
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+              const uint4 v = wv[kt][blk];
+              const uint4 lo = make_uint4(v.x & 0x0F0F0F0Fu, v.y & 0x0F0F0F0Fu, v.z & 0x0F0F0F0Fu, v.w & 0x0F0F0F0Fu);
+              const uint4 hi = make_uint4((v.x >> 4) & 0x0F0F0F0Fu, (v.y >> 4) & 0x0F0F0F0Fu, (v.z >> 4) & 0x0F0F0F0Fu, (v.w >> 4) & 0x0F0F0F0Fu);
+              *reinterpret_cast<uint4*>(dst + kt * A_TILE + r * 64 + (((2 * blk) ^ a_sw) << 4)) = lo;
+              *reinterpret_cast<uint4*>(dst + kt * A_TILE + r * 64 + (((2 * blk + 1) ^ a_sw) << 4)) = hi;
+            }
+          }
         fence_proxy_async();             // generic-proxy writes -> tcgen05.mma (async proxy) reads
         mbar_arrive(afull(s));
         mbar_arrive(kempty(s));
+      }
+    }
+  } else if (EPI == C1_RES && warp == RES_WARP) {
+    // =============================================================================== residual loader (case-1 epilogue operand)
+    // its own warp: waiting for a free buffer must stall neither the activation loads nor the converters
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (elect_one()) {
+      for (int t = 0; t < my_tiles; ++t) {
+        const int rb = t & 1;
+        mbar_wait_small(rempty(rb), ((t >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(rfull(rb), RES_BYTES);
+        tma_load_3d(smem_base + p.off_res + rb * RES_BYTES, &maps.res, 0, (slot + t * p.ctas_per_n) * 128, n0 / 64, rfull(rb));
       }
     }
   } else if (warp == MMA_WARP) {

@@ -320,7 +320,7 @@ class FakeQuantResNet:
 
     def _act(self, name, *args, **kw):
         out = self.acts[name](*args, **kw)
-        if self.trace is not None:
+        if self.trace is not None and (self.trace_names is None or name in self.trace_names):
             self.trace[name] = torch.round(out[0] / out[1].view(-1)).to(torch.int64)
         return out
 
@@ -351,8 +351,10 @@ class FakeQuantResNet:
 
     @torch.no_grad()
     def forward(self, x, trace=False):
-        """Q_ResNet50.forward q_resnet.py:114-135 (== Q_ResNet18.forward :53-74)."""
+        """Q_ResNet50.forward q_resnet.py:114-135 (== Q_ResNet18.forward :53-74).  trace: False, True (every QuantAct output as
+        integers) or a collection of QuantAct names (only those: the full trace of a batch of 128 is several GB)."""
         self.trace = {} if trace else None
+        self.trace_names = None if trace is True or not trace else set(trace)
         x, a_sf = self._act("quant_input", x)
         x, w_sf = self.convs[self.init_name](x, a_sf)
         x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)

@@ -142,3 +142,46 @@ def test_compiled_graph_uint8_pixels_equal_the_torch_pipeline():
         assert not torch.equal(changed, want)
         q.load_state_dict(sd)
         assert torch.equal(q(x.to(DEV)).cpu(), want)
+
+
+# BASELINE.json configurations 1-4 at the batch sizes that are benchmarked (config 5 = config "resnet50 uniform4" per GPU)
+BENCH_CONFIGS = [("resnet18", "uniform8", 8), ("resnet18", "uniform4", 128), ("resnet50", "uniform8", 128),
+                 ("resnet50", "bops_0.5", 128), ("resnet50", "uniform4", 128), ("resnet50", "uniform8", 8)]
+
+
+@pytest.mark.parametrize("arch,scheme,batch", BENCH_CONFIGS)
+def test_benchmarked_configuration_matches_oracle_on_every_row(arch, scheme, batch):
+    """The configuration bench.py times (CUDA graph, fused kernels, uint16 stream) at the benchmarked batch size against the
+    oracle (the reference's fake-quant forward restated on the CPU, oracle/fakequant.py): ALL rows of the logits bit-equal, and the
+    integers of the residual stream at the end of stage 1 and of the last stage (eager pass with the same kernels) equal too.
+    Late tiles of the persistent kernels (many tiles per CTA, barrier phase flips, TMEM double buffering) are only reached at this size."""
+    _, meta = load_net_golden(arch, scheme)
+    x = synthetic_batch(batch, 11)
+    fqm = build_fakequant(arch, scheme, meta)
+    n_stage = len(fqm.units_per_stage)
+    probes = ["stage1.unit%d.quant_act_int32" % fqm.units_per_stage[0], "stage%d.unit%d.quant_act_int32" % (n_stage, fqm.units_per_stage[-1])]
+    want_logits = fqm(x, trace=probes).numpy()
+    want = {k: np.maximum(v.numpy(), 0) for k, v in fqm.trace.items()}            # the stream is stored after the unit's ReLU
+    s_in = np.float32(meta["acts"]["quant_input"]["scale"])
+    q_in = torch.from_numpy(ir.quantize_input(x.numpy(), s_in).astype(np.int8)).to(DEV)      # NHWC int8
+    q = _model(arch, scheme, meta)
+    eng = hb.compile_model(q, q_in)
+    got = eng(q_in).cpu().numpy()
+    assert eng.fallbacks == 0
+    assert got.shape == want_logits.shape and np.array_equal(got, want_logits), \
+        "rows differing from the oracle: %s" % np.nonzero((got != want_logits).any(axis=1))[0][:16].tolist()
+    # residual-stream integers, eager pass through the same kernels
+    rec = {}
+    for name, m in q.named_modules():
+        if isinstance(m, hb.q_resnet.QResidualUnit) and (name + ".quant_act_int32") in want:
+            m.register_forward_hook(lambda mod, inp, out, name=name: rec.__setitem__(name + ".quant_act_int32", out[0]))
+    n, h, w, c = q_in.shape
+    hb.ops.reset_status(0)
+    with torch.no_grad(), qtensor.engine_mode(residual_bits=16, checked=True):
+        q(hb.IntActivation(qtensor.Node("int", (n, c, h, w), data=q_in.view(-1), bits=8, signed=True), q_in.device))
+    torch.cuda.synchronize()
+    assert hb.ops.get_status(0) & 7 == 0
+    assert set(rec) == set(want)
+    for name, t in rec.items():
+        g = t.int_tensor().cpu().numpy()
+        assert np.array_equal(g, want[name]), (name, int((g != want[name]).sum()))
