@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include "conv1x1.h"
+#include "conv_dual.h"
 #include "conv_halo.h"
 #include "conv_igemm.cuh"
 #include "conv_tc.cuh"
@@ -23,7 +24,7 @@ struct hawq_handle {
 };
 
 static thread_local char g_err[512] = "";
-static long long g_kernel_count[4] = {0, 0, 0, 0};   // hawq_debug_kernel_count: launches by kernel family (not atomic: debugging aid)
+static long long g_kernel_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // hawq_debug_kernel_count: launches by kernel family (not atomic: debugging aid)
 
 // ---- TMA tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda)
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -178,6 +179,7 @@ int hawq_create(int device, hawq_handle** out) {
     return rc;
   if ((rc = halo_set_attributes())) return fail(rc, "%s", halo_last_error());
   if ((rc = c1_set_attributes())) return fail(rc, "%s", c1_last_error());
+  if ((rc = dual_set_attributes())) return fail(rc, "%s", dual_last_error());
   CUDA_TRY(cudaFuncSetAttribute(linear_dp4a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, linear_smem_bytes(LIN_MAX_K)));
   if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
       (rc = set_conv_attr<64, true>()))
@@ -417,6 +419,12 @@ int hawq_conv2d_dual(hawq_handle* h, const hawq_conv_desc* d, const hawq_epilogu
   const long long M = (long long)d->N * d->H * d->W;
   if (M > 0x7fffff00ll || (long long)d2->N * d2->H * d2->W > 0x7fffff00ll) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_conv2d_dual: too many pixels");
 
+  {   // int8 resize units: stationary weights, strided identity rows by TMA (conv_dual.cuh)
+    const int dr = launch_conv_dual(h->sm_count, d, ep, x, w, chan, d2, x2, w2, chan2, out, out_low, h->status, sat_pack_enabled() ? 1 : 0, stream);
+    if (dr < 0) return fail(dr, "%s", dual_last_error());
+    if (dr == 0) { ++g_kernel_count[4]; return launch_check("conv_dual"); }
+  }
+  ++g_kernel_count[5];
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.x = (const uint8_t*)x; p.w = w; p.chan = chan; p.out = out; p.out_low = out_low; p.status = h->status;
@@ -647,6 +655,6 @@ int hawq_retile_weights(hawq_handle* h, const int8_t* w_ohwi, int32_t Cout, int6
 
 int32_t hawq_debug_halo_trace(int64_t* host_out, int32_t n) { return halo_read_trace(reinterpret_cast<long long*>(host_out), n); }
 
-int64_t hawq_debug_kernel_count(int32_t family) { return (family >= 0 && family < 4) ? g_kernel_count[family] : -1; }
+int64_t hawq_debug_kernel_count(int32_t family) { return (family >= 0 && family < 8) ? g_kernel_count[family] : -1; }
 
 }  // extern "C"

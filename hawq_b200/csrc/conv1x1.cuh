@@ -87,10 +87,10 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
   if (tid == 0) {
     mbar_init(b_full, 1);
     for (int s = 0; s < C1_MAX_STAGES; ++s) {
-      mbar_init(afull(s), A4 ? 128 : 1);
+      mbar_init(afull(s), A4 ? 4 : 1);        // A4: one arrival per converter warp
       mbar_init(aempty(s), 1);
       mbar_init(kfull(s), 1);
-      mbar_init(kempty(s), 128);
+      mbar_init(kempty(s), 4);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull(b), 1);
@@ -182,8 +182,11 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
             }
           }
         fence_proxy_async();             // generic-proxy writes -> tcgen05.mma (async proxy) reads
-        mbar_arrive(afull(s));
-        mbar_arrive(kempty(s));
+        __syncwarp();
+        if (lane == 0) {                 // one arrival per warp (128 arrivals on one barrier word serialise)
+          mbar_arrive(afull(s));
+          mbar_arrive(kempty(s));
+        }
       }
     }
   } else if (EPI == C1_RES && warp == RES_WARP) {

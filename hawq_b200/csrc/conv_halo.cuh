@@ -95,10 +95,10 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
   if (tid == 0) {
     mbar_init(b_full, 1);
     for (int b = 0; b < HALO_MAX_BUFS; ++b) {
-      mbar_init(pfull(b), A4 ? 128 : 1);
+      mbar_init(pfull(b), A4 ? 4 : 1);        // A4: one arrival per converter warp
       mbar_init(pempty(b), 1);
       mbar_init(kfull(b), 1);
-      mbar_init(kempty(b), 128);
+      mbar_init(kempty(b), 4);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull(b), 1);
@@ -189,8 +189,11 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
           }
         }
         fence_proxy_async();             // generic-proxy writes -> tcgen05.mma (async proxy) reads
-        mbar_arrive(pfull(b));
-        mbar_arrive(kempty(kb));
+        __syncwarp();
+        if (lane == 0) {                 // one arrival per warp (128 arrivals on one barrier word serialise)
+          mbar_arrive(pfull(b));
+          mbar_arrive(kempty(kb));
+        }
       }
     }
   } else if (warp == MMA_WARP) {

@@ -132,7 +132,7 @@ def latency_table_from_detail(detail4, detail8, arch, parameters):
             l = next(launches)
             if not resize:
                 lat[idx[u + "." + last]] = l["ms"]
-            elif l["kernel"] in ("hawq_conv2d_dual", "conv_tc_dual"):
+            elif l["kernel"] in ("hawq_conv2d_dual", "conv_tc_dual", "conv_dual"):
                 a, b = idx[u + "." + last], idx[u + ".quant_identity_convbn"]
                 w = parameters[a] / (parameters[a] + parameters[b])
                 lat[a], lat[b] = l["ms"] * w, l["ms"] * (1 - w)

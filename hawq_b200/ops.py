@@ -149,6 +149,7 @@ def conv2d_dual(x, desc, ep, w, chan, desc2, x2, w2, chan2, out=None, out_low=No
     """resize unit: identity 1x1 conv (desc2/x2/w2/chan2) + last 1x1 conv (desc/x/w/chan) + case-1 sum in one kernel."""
     h, s = _ctx(x)
     ev = _begin()
+    k0 = _lib.load().hawq_debug_kernel_count(4) if ev is not None else 0
     _lib.check(_lib.load().hawq_conv2d_dual(h, C.byref(desc), C.byref(ep), _p(x), _p(w), _p(chan), C.byref(desc2), _p(x2), _p(w2),
                                             _p(chan2), _p(out), _p(out_low), s))
     work = None
@@ -158,7 +159,7 @@ def conv2d_dual(x, desc, ep, w, chan, desc2, x2, w2, chan2, out=None, out_low=No
         b = (m * (desc.Cin + desc2.Cin) * desc.a_bits // 8 + desc.Cout * (desc.Cin + desc2.Cin) + 32 * desc.Cout
              + m * desc.Cout * (ep.y_bits + ep.low_bits) // 8)
         work = (macs, b)
-    _count("conv_tc_dual", work, ev)
+    _count("conv_dual" if ev is not None and _lib.load().hawq_debug_kernel_count(4) != k0 else "conv_tc_dual", work, ev)
 
 
 def linear(x, w, chan, fscale, out, n, k, cout, cout_pad):

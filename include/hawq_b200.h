@@ -212,7 +212,8 @@ int hawq_permute_weights_for_i4(int8_t* host_w, int64_t rows_times_taps, int32_t
 int hawq_retile_weights(hawq_handle* h, const int8_t* w_ohwi, int32_t Cout, int64_t K, int8_t* out, void* stream);
 /* debug: number of hawq_conv2d launches so far that went to kernel family 0 = conv_tc (generic tcgen05 implicit GEMM),
  * 1 = conv_halo (3x3 stride-1, A operand read in place), 2 = conv_halo launches that needed the 2-D weight-map fallback,
- * 3 = conv1x1 (1x1 stride-1, stationary weights);
+ * 3 = conv1x1 (1x1 stride-1, stationary weights), 4 = conv_dual (resize-unit tail, stationary weights), 5 = resize-unit tails
+ * on conv_tc;
  * -1 for an unknown family.  Lets tests assert which kernel ran. */
 int64_t hawq_debug_kernel_count(int32_t family);
 /* debug: with HAWQ_B200_HALO_TRACE=1 in the environment every conv_halo launch records clock64 stamps of CTA 0

@@ -527,3 +527,50 @@ def test_conv1x1_requant_and_residual(geom, a_bits):
         for a, b, k_ in zip(cs, gs, keys):
             assert torch.equal(a, b), (geom, a_bits, flag, low_bits, k_)
     ops.reset_status(0)
+
+
+# ------------------------------------------------------------------------------------------------ conv_dual (stationary weights)
+DUALK_GEOMS = [
+    # N, Ho, Wo, Cin (last conv), Cin2 (identity conv), Cout, identity stride   (identity input = s * Ho x s * Wo)
+    (2, 56, 56, 64, 64, 256, 1),        # ResNet-50 stage 1: linear 128-row tiles, both operands by plain boxes
+    (3, 28, 28, 128, 256, 512, 2),      # stage 2: tiles of 4 output rows (112), identity rows by the strided 5-D box
+    (2, 14, 14, 256, 512, 1024, 2),     # stage 3: 7 rows (98)
+    (5, 7, 7, 512, 1024, 2048, 2),      # stage 4: two images per tile (98), odd batch -> half-empty last tile; BN = 64
+    (2, 12, 12, 64, 128, 192, 2),       # Cout = 192 -> BN = 64, tiles of 6 rows (72)
+    (9, 4, 4, 64, 64, 128, 2),          # eight images per tile
+]
+
+
+@pytest.mark.parametrize("flag", [1, 2])
+@pytest.mark.parametrize("geom", DUALK_GEOMS)
+def test_conv_dual_stationary_weights(geom, flag):
+    """int8 resize-unit tails take conv_dual.cuh (counter 4): bit-exact vs RAW_I32 identity conv + res_kind-1 RESIDUAL conv of the ABI model."""
+    from hawq_b200 import _lib
+    n, ho, wo, cin, cin2, cout, s2 = geom
+    r = rng(31337 + sum(v * (i + 3) for i, v in enumerate(geom)) * 4 + flag)
+    h2, w2 = ho * s2, wo * s2
+    numel = n * ho * wo * cout
+    x = rand_act(r, n * ho * wo * cin, 8)
+    x2 = rand_act(r, n * h2 * w2 * cin2, 8)
+    wt = torch.from_numpy(r.randint(-8, 8, size=(cout, 1, 1, cin)).astype(np.int8))
+    wt2 = torch.from_numpy(r.randint(-8, 8, size=(cout, 1, 1, cin2)).astype(np.int8))
+    hi = 0.9 if flag == 1 else 30.0
+    chan = make_chan(r, cout, bias_mag=3000, ratio_lo=1e-2, ratio_hi=hi)
+    chan2 = make_chan(r, cout, bias_mag=3000, ratio_lo=1e-2, ratio_hi=hi)
+    d = ops.conv_desc(n, ho, wo, cin, cout, 1, 1, 1, 0, 8, 1)
+    d2 = ops.conv_desc(n, h2, w2, cin2, cout, 1, 1, s2, 0, 8, 1)
+    wg, wg2 = ops.upload_weights(wt, DEV), ops.upload_weights(wt2, DEV)
+    for low_bits in (8, 4, 0):
+        ep = ops.epilogue(EPI_RESIDUAL, relu=1, res_kind=1, res_bits=32, y_bits=16, low_bits=low_bits, low_me=dyadic(0.003),
+                          low_clamp=(0, 15) if low_bits == 4 else (-128, 127), flags=flag)
+        args = dict(x=x, desc=d, ep=ep, w=wt, chan=chan, desc2=d2, x2=x2, w2=wt2, chan2=chan2, out=out_buf(numel, 16),
+                    out_low=out_buf(numel, low_bits) if low_bits else None)
+        keys = ["out"] + (["out_low"] if low_bits else [])
+        ops.reset_status(0)
+        before = _lib.load().hawq_debug_kernel_count(4)
+        cs, gs = run_both("conv2d_dual", args, keys, gpu_overrides=dict(w=wg, w2=wg2))
+        assert _lib.load().hawq_debug_kernel_count(4) == before + 1, "conv_dual did not take this launch"
+        assert ops.get_status(0) & 6 == 0
+        for a, b, k_ in zip(cs, gs, keys):
+            assert torch.equal(a, b), (geom, flag, low_bits, k_)
+    ops.reset_status(0)

@@ -12,6 +12,9 @@ for what in "$@"; do
     c1)
       timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "conv1x1" > gpurun_out/pytest_c1.log 2>&1
       echo "c1 exit $?"; tail -15 gpurun_out/pytest_c1.log;;
+    dualk)
+      timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "dual" > gpurun_out/pytest_dual.log 2>&1
+      echo "dual exit $?"; tail -15 gpurun_out/pytest_dual.log;;
     halo)
       timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "halo" > gpurun_out/pytest_halo.log 2>&1
       echo "halo exit $?"; tail -15 gpurun_out/pytest_halo.log;;

@@ -54,7 +54,7 @@ def main():
         print(line)
     fams = OrderedDict()
     for k, a in agg.items():
-        name = "conv_tc_kernel" if "conv_tc_kernel" in k else "conv_halo_kernel" if "conv_halo_kernel" in k else "conv1x1_kernel" if "conv1x1_kernel" in k else None
+        name = "conv_tc_kernel" if "conv_tc_kernel" in k else "conv_halo_kernel" if "conv_halo_kernel" in k else "conv1x1_kernel" if "conv1x1_kernel" in k else "conv_dual_kernel" if "conv_dual_kernel" in k else None
         if name is None:
             continue
         fam = fams.setdefault(name, {"launches": 0, "us": 0.0, "rd": 0.0, "wr": 0.0})
