@@ -386,7 +386,7 @@ def roofline_leg(hb, ops, q, dev_pool, a, graph_ms_per_step):
     # kernel families: conv_tc (+ its dual-accumulator instantiation) is one template; conv_halo is the in-place 3x3 kernel
     fam = {}
     for k, g in agg.items():
-        f = fam.setdefault("conv_tc_kernel" if k.startswith("conv_tc") else ("conv_halo_kernel" if k == "conv_halo" else "conv1x1_kernel" if k == "conv1x1" else "conv_dual_kernel" if k == "conv_dual" else k),
+        f = fam.setdefault("conv_tc_kernel" if k.startswith("conv_tc") else ("conv_halo_kernel" if k == "conv_halo" else "conv1x1_kernel" if k == "conv1x1" else "conv_dual_kernel" if k == "conv_dual" else "stem_tc_kernel" if k == "stem_tc" else k),
                            {"ms": 0.0, "bytes": 0, "macs": 0, "launches": 0})
         for key in f:
             f[key] += g[key]

@@ -66,6 +66,7 @@ SIGNATURES = {
                                 C.POINTER(hawq_conv_desc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "hawq_linear_i8": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hawq_stem_conv_i8": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "hawq_stem_pool_i8": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _u32, _i32, _i32, _i32, _vp, _vp]),
     "hawq_maxpool_requant": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _u32, _i32, _i32, _i32, _vp, _vp]),
     "hawq_avgpool_requant": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _u32, _i32, _i32, _i32, _vp, _vp]),
     "hawq_quantize_input_f32": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _f32, _i32, _i32, _vp, _vp]),
@@ -81,6 +82,7 @@ SIGNATURES = {
     "hawq_retile_weights": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "hawq_debug_kernel_count": (_i64, [_i32]),
     "hawq_debug_halo_trace": (_i32, [_vp, _i32]),
+    "hawq_debug_c1_trace": (_i32, [_vp, _i32]),
     "hawq_workspace_bytes": (_i64, [C.POINTER(hawq_conv_desc), C.POINTER(hawq_epilogue_desc)]),
 }
 

@@ -14,6 +14,7 @@
 #include "conv_tc.cuh"
 #include "elementwise.cuh"
 #include "stem.cuh"
+#include "stem_tc.h"
 
 using namespace hawq;
 
@@ -180,6 +181,7 @@ int hawq_create(int device, hawq_handle** out) {
   if ((rc = halo_set_attributes())) return fail(rc, "%s", halo_last_error());
   if ((rc = c1_set_attributes())) return fail(rc, "%s", c1_last_error());
   if ((rc = dual_set_attributes())) return fail(rc, "%s", dual_last_error());
+  if ((rc = stem_tc_set_attributes())) return fail(rc, "%s", stem_tc_last_error());
   CUDA_TRY(cudaFuncSetAttribute(linear_dp4a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, linear_smem_bytes(LIN_MAX_K)));
   if ((rc = set_conv_attr<128, false>()) || (rc = set_conv_attr<64, false>()) || (rc = set_conv_attr<128, true>()) ||
       (rc = set_conv_attr<64, true>()))
@@ -507,6 +509,23 @@ int hawq_stem_conv_i8(hawq_handle* h, int32_t N, int32_t H, int32_t W, const int
   return launch_check("stem_conv");
 }
 
+int hawq_stem_pool_i8(hawq_handle* h, int32_t N, int32_t H, int32_t W, const int8_t* x, const int8_t* w256, const hawq_chan* chan,
+                      int32_t clamp_lo, int32_t clamp_hi, int32_t y_bits, void* y, int32_t low_bits, uint32_t low_m, int32_t low_e,
+                      int32_t low_lo, int32_t low_hi, void* out_low, void* stream) {
+  if (!h || !x || !w256 || !chan || !y) return fail(HAWQ_ERR_BAD_ARG, "hawq_stem_pool_i8: null argument");
+  if (N < 1 || H < 7 || W < 7) return fail(HAWQ_ERR_BAD_ARG, "hawq_stem_pool_i8: bad geometry");
+  if (clamp_lo < -32768 || clamp_hi > 32767 || clamp_lo > clamp_hi) return fail(HAWQ_ERR_BAD_ARG, "hawq_stem_pool_i8: clamp must fit int16");
+  if ((y_bits != 16 && y_bits != 32) || (low_bits != 0 && low_bits != 4 && low_bits != 8) || (low_bits && !out_low))
+    return fail(HAWQ_ERR_BAD_ARG, "hawq_stem_pool_i8: bad output description");
+  if (low_bits) { int rc = check_me(low_m, low_e, "hawq_stem_pool_i8"); if (rc) return rc; }
+  const int r = launch_stem_tc(h->sm_count, N, H, W, x, w256, chan, clamp_lo, clamp_hi, y_bits, y, low_bits, low_m, low_e, low_lo, low_hi, out_low,
+                               h->status, stream);
+  if (r < 0) return fail(r, "%s", stem_tc_last_error());
+  if (r == 1) return fail(HAWQ_ERR_UNSUPPORTED, "hawq_stem_pool_i8: shape / ratio outside the fused kernel (use hawq_stem_conv_i8 + hawq_maxpool_requant)");
+  ++g_kernel_count[6];
+  return launch_check("stem_tc");
+}
+
 int hawq_maxpool_requant(hawq_handle* h, int32_t N, int32_t H, int32_t W, int32_t C, const int16_t* x, int32_t y_bits,
                          void* y, int32_t low_bits, uint32_t low_m, int32_t low_e, int32_t low_lo, int32_t low_hi,
                          void* out_low, void* stream) {
@@ -654,6 +673,7 @@ int hawq_retile_weights(hawq_handle* h, const int8_t* w_ohwi, int32_t Cout, int6
 }
 
 int32_t hawq_debug_halo_trace(int64_t* host_out, int32_t n) { return halo_read_trace(reinterpret_cast<long long*>(host_out), n); }
+int32_t hawq_debug_c1_trace(int64_t* host_out, int32_t n) { return c1_read_trace(reinterpret_cast<long long*>(host_out), n); }
 
 int64_t hawq_debug_kernel_count(int32_t family) { return (family >= 0 && family < 8) ? g_kernel_count[family] : -1; }
 

@@ -9,6 +9,15 @@
 namespace hawq {
 
 static thread_local char g_c1_err[256] = "";
+static long long* g_c1_trace = nullptr;        // device buffer [4][48][4], allocated on first use when HAWQ_B200_HALO_TRACE=1
+
+int c1_read_trace(long long* host_out, int n) {
+  if (!g_c1_trace) return 0;
+  if (n > 4 * 48 * 4) n = 4 * 48 * 4;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host_out, g_c1_trace, sizeof(long long) * n, cudaMemcpyDeviceToHost);
+  return n;
+}
 const char* c1_last_error() { return g_c1_err; }
 
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -151,6 +160,10 @@ int launch_conv1x1(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_de
   p.res_m = ep->res_m; p.res_e = ep->res_e; p.low_bits = ep->low_bits; p.low_m = ep->low_m; p.low_e = ep->low_e;
   p.low_lo = ep->low_lo; p.low_hi = ep->low_hi; p.sat_pack = sat_pack;
 
+  static const bool tracing = [] { const char* e = getenv("HAWQ_B200_HALO_TRACE"); return e && e[0] == '1'; }();
+  if (tracing && !g_c1_trace) cudaMalloc(&g_c1_trace, sizeof(long long) * 4 * 48 * 4);
+  if (tracing) cudaMemsetAsync(g_c1_trace, 0, sizeof(long long) * 4 * 48 * 4, (cudaStream_t)stream);
+  p.trace = tracing ? g_c1_trace : nullptr;
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) { snprintf(g_c1_err, sizeof(g_c1_err), "conv1x1: cuTensorMapEncodeTiled unavailable"); return HAWQ_ERR_CUDA; }
   C1Maps maps;

@@ -36,6 +36,7 @@ struct C1Params {
   int low_bits; uint32_t low_m; int low_e, low_lo, low_hi;     // RESIDUAL: low-bit copy
   int sat_pack;
   int off_a, off_packed, off_res, off_y, off_low, off_cst, off_bar;   // shared-memory carve-up (weights at 0)
+  long long* trace;          // debug timeline (HAWQ_B200_HALO_TRACE=1): [4 roles][48 tiles][4] clock64 stamps of CTA 0, or null
 };
 
 constexpr int C1_EPI_WARPS = 16;
@@ -79,6 +80,9 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_bar + 8 * (9 + 4 * C1_MAX_STAGES));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  auto stamp = [&](int role, int idx, int ev) {      // roles: 0 producer / converter, 1 MMA, 2 epilogue, 3 residual loader
+    if (p.trace != nullptr && blockIdx.x == 0 && idx < 48) p.trace[(role * 48 + idx) * 4 + ev] = clock64();
+  };
   const int nt = blockIdx.x % p.n_tiles, slot = blockIdx.x / p.n_tiles;
   const int n0 = nt * BN;
   const int my_tiles = (slot < p.m_tiles) ? (p.m_tiles - 1 - slot) / p.ctas_per_n + 1 : 0;
@@ -124,7 +128,9 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
         for (int t = 0; t < my_tiles; ++t) {
           const int m0 = (slot + t * p.ctas_per_n) * 128;
           for (int k0 = 0; k0 < p.KT; k0 += p.KC) {
+            if (k0 == 0) stamp(0, t, 0);
             mbar_wait_small(aempty(s), ph ^ 1);
+            if (k0 == 0) stamp(0, t, 1);
             mbar_arrive_expect_tx(afull(s), stage_bytes);
             tma_load_3d(smem_base + p.off_a + s * (uint32_t)(p.KC * A_TILE), &maps.a, 0, m0, k0, afull(s));
             if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1; }
@@ -154,8 +160,12 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
           __syncwarp();
         }
         const int s = g % p.NS;
+        const bool st0 = tid == 0 && g % stages_per_tile == 0;
+        if (st0) stamp(0, g / stages_per_tile, 0);
         mbar_wait_small(kfull(s), (g / p.NS) & 1);
+        if (st0) stamp(0, g / stages_per_tile, 1);
         mbar_wait_small(aempty(s), ((g / p.NS) & 1) ^ 1);
+        if (st0) stamp(0, g / stages_per_tile, 2);
         const uint8_t* src = smem + p.off_packed + s * (p.KC * A_TILE / 2);
         uint8_t* dst = smem + p.off_a + s * (p.KC * A_TILE);
         const int r = tid;                                      // one row per thread, every k-tile of the stage
@@ -187,6 +197,7 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
           mbar_arrive(afull(s));
           mbar_arrive(kempty(s));
         }
+        if (st0) stamp(0, g / stages_per_tile, 3);
       }
     }
   } else if (EPI == C1_RES && warp == RES_WARP) {
@@ -196,7 +207,9 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
     if (elect_one()) {
       for (int t = 0; t < my_tiles; ++t) {
         const int rb = t & 1;
+        stamp(3, t, 0);
         mbar_wait_small(rempty(rb), ((t >> 1) & 1) ^ 1);
+        stamp(3, t, 1);
         mbar_arrive_expect_tx(rfull(rb), RES_BYTES);
         tma_load_3d(smem_base + p.off_res + rb * RES_BYTES, &maps.res, 0, (slot + t * p.ctas_per_n) * 128, n0 / 64, rfull(rb));
       }
@@ -214,13 +227,16 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
       uint32_t s = 0, ph = 0, a0 = a_base;
       for (int t = 0; t < my_tiles; ++t) {
         const uint32_t buf = t & 1;
+        stamp(1, t, 0);
         mbar_wait_small(tempty(buf), ((t >> 1) & 1) ^ 1);
         tc_fence_after();
+        stamp(1, t, 1);
         const uint32_t d_tmem = tmem_base + buf * BN;
         uint32_t wl = w_base;
         for (int k0 = 0; k0 < p.KT; k0 += p.KC) {
           mbar_wait_small(afull(s), ph);
           tc_fence_after();
+          if (k0 == 0) stamp(1, t, 2);
           uint32_t al = a0;
           if (k0 == 0) umma_i8_lohi<false>(d_tmem, al, wl, desc_hi, idesc);
           else umma_i8_lohi<true>(d_tmem, al, wl, desc_hi, idesc);
@@ -236,6 +252,7 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
           if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1; a0 = a_base; }
         }
         umma_commit(tfull(buf));
+        stamp(1, t, 3);
       }
     }
   } else {
@@ -340,6 +357,7 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
       const uint32_t r_chunk = (uint32_t)(cg * CW) / 64, r_piece0 = ((uint32_t)(cg * CW) % 64) / 8;
       for (int t = 0; t < my_tiles; ++t) {
         const uint32_t buf = t & 1;
+        if (elect_x) stamp(2, t, 0);
         mbar_wait_small(rfull(buf), (t >> 1) & 1);
         const uint8_t* rrow = smem + p.off_res + buf * RES_BYTES + r_chunk * (128 * 128) + row * 128;
         uint4 rv[CW / 8];
@@ -354,6 +372,7 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
         if constexpr (CW == 32) tmem_ld32(taddr, acc);
         else tmem_ld16(taddr, acc);
         tmem_ld_wait();
+        if (elect_x) stamp(2, t, 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(buf));
@@ -407,6 +426,7 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
         __syncwarp();
         if (lane == 0) mbar_arrive(rempty(buf));
         // stage y ([64-column chunk][128 rows][128 B], SWIZZLE_128B) and the low-bit tile; one TMA store each per tile
+        if (elect_x) stamp(2, t, 2);
         if (elect_x) bulk_wait_read_all();                        // the previous tile's stores have finished reading the staging tiles
         asm volatile("bar.sync 1, %0;" ::"n"(C1_EPI_WARPS * 32));
         uint8_t* yt = smem + p.off_y + r_chunk * (128 * 128);
@@ -435,6 +455,7 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
           tma_store_3d(&maps.y, 0, m0, n0 / 64, smem_base + p.off_y);
           if (p.low_bits) tma_store_2d(&maps.low, n0 * p.low_bits / 8, m0, smem_base + p.off_low);
           bulk_commit();
+          stamp(2, t, 3);
         }
       }
       if (elect_x) bulk_wait_all();

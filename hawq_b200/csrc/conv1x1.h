@@ -9,6 +9,7 @@ namespace hawq {
 int launch_conv1x1(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_desc* ep, const void* x, const int8_t* w_ohwi,
                    const hawq_chan* chan, const void* res, void* out, void* out_low, int32_t* status, int sat_pack, void* stream);
 int c1_set_attributes();
+int c1_read_trace(long long* host_out, int n);   // debug timeline of the last conv1x1 launch (HAWQ_B200_HALO_TRACE=1)
 const char* c1_last_error();
 
 }  // namespace hawq

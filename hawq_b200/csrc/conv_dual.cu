@@ -40,7 +40,7 @@ struct DualPlan {
   DualParams p;
 };
 
-static bool plan_for(int bn, int KT1, int KT2, int low_bits, DualPlan* out) {
+static bool plan_for(int bn, bool a4, int KT1, int KT2, int low_bits, DualPlan* out) {
   DualParams& p = out->p;
   const int w_bytes = (KT1 + KT2) * bn * 64;
   const int y_bytes = 128 * bn * 2, low_bytes = low_bits ? 128 * bn : 0;
@@ -52,6 +52,7 @@ static bool plan_for(int bn, int KT1, int KT2, int low_bits, DualPlan* out) {
     for (int ns = (kc == 4 ? 3 : DUAL_MAX_STAGES); ns >= 2; --ns) {
       int off = round_up(w_bytes, 1024);
       p.off_a = off; off += ns * a_stage + 8192;        // + slack: the MMA reads 128 rows from k-tile blocks of TR rows
+      p.off_packed = off; off += a4 ? ns * (a_stage / 2) : 0;
       p.off_y = off; off += y_bytes;
       p.off_low = off; off += low_bytes;
       p.off_cst = off; off += cst;
@@ -70,23 +71,27 @@ static bool plan_for(int bn, int KT1, int KT2, int low_bits, DualPlan* out) {
 
 int dual_set_attributes() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(conv_dual_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(conv_dual_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(conv_dual_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(conv_dual_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess) {
+  if ((e = cudaFuncSetAttribute(conv_dual_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_dual_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_dual_kernel<128, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_dual_kernel<64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_dual_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_dual_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_dual_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(conv_dual_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DUAL_SMEM_MAX)) != cudaSuccess) {
     snprintf(g_dual_err, sizeof(g_dual_err), "conv_dual: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return HAWQ_ERR_CUDA;
   }
   return HAWQ_OK;
 }
 
-template <int BN, bool WIDE>
+template <int BN, bool WIDE, bool A4>
 static void launch(const DualPlan& plan, const DualMaps& maps, int grid, cudaStream_t st) {
   static const bool pdl = [] { const char* e = getenv("HAWQ_B200_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(DUAL_THREADS, 1, 1);
+  cfg.blockDim = dim3(dual_threads(A4), 1, 1);
   cfg.dynamicSmemBytes = (size_t)plan.total;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -94,7 +99,7 @@ static void launch(const DualPlan& plan, const DualMaps& maps, int grid, cudaStr
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, conv_dual_kernel<BN, WIDE>, plan.p, maps);
+  cudaLaunchKernelEx(&cfg, conv_dual_kernel<BN, WIDE, A4>, plan.p, maps);
 }
 
 #define ENC(map, rank, base, dims, strides, box, estr, sw, what)                                                                        \
@@ -112,7 +117,9 @@ int launch_conv_dual(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_
                      void* out, void* out_low, int32_t* status, int sat_pack, void* stream) {
   static const bool enabled = [] { const char* e = getenv("HAWQ_B200_DUALK"); return !(e && e[0] == '0'); }();   // debugging switch
   if (!enabled) return 1;
-  if (d->a_bits != 8 || d2->a_bits != 8) return 1;
+  if ((d->a_bits != 8 && d->a_bits != 4) || d2->a_bits != d->a_bits) return 1;
+  const bool a4 = d->a_bits == 4;
+  const cuuint64_t ktb = a4 ? 32 : 64;                 // bytes of one k-tile (64 channels) in an activation row
   const bool one = (ep->flags & HAWQ_EP_RATIOS_LE_ONE) != 0;
   const bool wide = !one && (ep->flags & HAWQ_EP_RATIOS_LE_2P20) != 0;
   if (!one && !wide) return 1;
@@ -132,7 +139,7 @@ int launch_conv_dual(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_
   const int KT1 = d->Cin / 64, KT2 = d2->Cin / 64;
   DualPlan plan;
   memset(&plan, 0, sizeof(plan));
-  if (!((d->Cout % 128 == 0 && plan_for(128, KT1, KT2, ep->low_bits, &plan)) || plan_for(64, KT1, KT2, ep->low_bits, &plan))) return 1;
+  if (!((d->Cout % 128 == 0 && plan_for(128, a4, KT1, KT2, ep->low_bits, &plan)) || plan_for(64, a4, KT1, KT2, ep->low_bits, &plan))) return 1;
   DualParams& p = plan.p;
   p.chan = chan; p.chan2 = chan2; p.status = status;
   p.M = (int)M; p.Cout = d->Cout; p.KT1 = KT1; p.KT2 = KT2; p.TR = TR;
@@ -150,25 +157,26 @@ int launch_conv_dual(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_
   memset(&maps, 0, sizeof(maps));
   const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   bool strict = true;
+  const CUtensorMapSwizzle sw_a = a4 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
   {
-    const cuuint64_t dims[3] = {64, (cuuint64_t)M, (cuuint64_t)KT1};
-    const cuuint64_t strides[2] = {(cuuint64_t)d->Cin, 64};
-    const cuuint32_t box[3] = {64u, (cuuint32_t)TR, (cuuint32_t)p.KC};
-    ENC(maps.a, 3, x, dims, strides, box, ones, CU_TENSOR_MAP_SWIZZLE_64B, "activations");
+    const cuuint64_t dims[3] = {ktb, (cuuint64_t)M, (cuuint64_t)KT1};
+    const cuuint64_t strides[2] = {(cuuint64_t)d->Cin * d->a_bits / 8, ktb};
+    const cuuint32_t box[3] = {(cuuint32_t)ktb, (cuuint32_t)TR, (cuuint32_t)p.KC};
+    ENC(maps.a, 3, x, dims, strides, box, ones, sw_a, "activations");
   }
   if (s2 == 1) {
-    const cuuint64_t dims[3] = {64, (cuuint64_t)M, (cuuint64_t)KT2};
-    const cuuint64_t strides[2] = {(cuuint64_t)d2->Cin, 64};
-    const cuuint32_t box[3] = {64u, (cuuint32_t)TR, (cuuint32_t)p.KC};
-    ENC(maps.a2, 3, x2, dims, strides, box, ones, CU_TENSOR_MAP_SWIZZLE_64B, "identity activations");
+    const cuuint64_t dims[3] = {ktb, (cuuint64_t)M, (cuuint64_t)KT2};
+    const cuuint64_t strides[2] = {(cuuint64_t)d2->Cin * d->a_bits / 8, ktb};
+    const cuuint32_t box[3] = {(cuuint32_t)ktb, (cuuint32_t)TR, (cuuint32_t)p.KC};
+    ENC(maps.a2, 3, x2, dims, strides, box, ones, sw_a, "identity activations");
   } else {
     strict = false;           // a driver that refuses the strided 5-D view: the caller falls back to conv_tc
-    const cuuint64_t c2 = (cuuint64_t)d2->Cin;
-    const cuuint64_t dims[5] = {64, (cuuint64_t)d2->W, (cuuint64_t)d2->H, (cuuint64_t)d2->N, (cuuint64_t)KT2};
-    const cuuint64_t strides[4] = {c2, c2 * d2->W, c2 * d2->W * d2->H, 64};
-    const cuuint32_t box[5] = {64u, (cuuint32_t)(2 * Wo), (cuuint32_t)(2 * R), (cuuint32_t)NI, (cuuint32_t)p.KC};
+    const cuuint64_t c2 = (cuuint64_t)d2->Cin * d->a_bits / 8;
+    const cuuint64_t dims[5] = {ktb, (cuuint64_t)d2->W, (cuuint64_t)d2->H, (cuuint64_t)d2->N, (cuuint64_t)KT2};
+    const cuuint64_t strides[4] = {c2, c2 * d2->W, c2 * d2->W * d2->H, ktb};
+    const cuuint32_t box[5] = {(cuuint32_t)ktb, (cuuint32_t)(2 * Wo), (cuuint32_t)(2 * R), (cuuint32_t)NI, (cuuint32_t)p.KC};
     const cuuint32_t estr[5] = {1, 2, 2, 1, 1};
-    ENC(maps.a2, 5, x2, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_64B, "strided identity activations");
+    ENC(maps.a2, 5, x2, dims, strides, box, estr, sw_a, "strided identity activations");
     strict = true;
   }
   {
@@ -199,8 +207,13 @@ int launch_conv_dual(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_
   }
   const int grid = p.n_tiles * p.ctas_per_n;
   cudaStream_t st = (cudaStream_t)stream;
-  if (plan.bn == 128) { if (wide) launch<128, true>(plan, maps, grid, st); else launch<128, false>(plan, maps, grid, st); }
-  else { if (wide) launch<64, true>(plan, maps, grid, st); else launch<64, false>(plan, maps, grid, st); }
+  if (a4) {
+    if (plan.bn == 128) { if (wide) launch<128, true, true>(plan, maps, grid, st); else launch<128, false, true>(plan, maps, grid, st); }
+    else { if (wide) launch<64, true, true>(plan, maps, grid, st); else launch<64, false, true>(plan, maps, grid, st); }
+  } else {
+    if (plan.bn == 128) { if (wide) launch<128, true, false>(plan, maps, grid, st); else launch<128, false, false>(plan, maps, grid, st); }
+    else { if (wide) launch<64, true, false>(plan, maps, grid, st); else launch<64, false, false>(plan, maps, grid, st); }
+  }
   return 0;
 }
 

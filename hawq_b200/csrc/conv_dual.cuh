@@ -9,7 +9,7 @@
 //     sub-sampling.  For that an output tile is R whole rows of one image (or NI whole images) = TR <= 128 rows; the k-tile
 //     blocks in shared memory are then TR * 64 B apart and the MMA (M = 128) reads past the block end: rows >= TR of the
 //     accumulator are garbage and never stored.
-// int8 activations only (packed 4-bit resize units stay on conv_tc.cuh).
+// A4: packed 4-bit activations ({32 B, ...} boxes) are expanded to int8 by four converter warps, once per stage.
 #pragma once
 #include "tc_ptx.cuh"
 
@@ -29,12 +29,13 @@ struct DualParams {
   int w1_boxes, w1_box_kt, w2_boxes, w2_box_kt;
   int low_bits; uint32_t low_m; int low_e, low_lo, low_hi;
   int sat_pack;
-  int off_a, off_y, off_low, off_cst, off_bar;   // shared-memory carve-up (weights at 0: [W1 | W2])
+  int off_a, off_packed, off_y, off_low, off_cst, off_bar;   // shared-memory carve-up (weights at 0: [W1 | W2])
 };
 
 constexpr int DUAL_EPI_WARPS = 16;
 constexpr int DUAL_MAX_STAGES = 4;
-constexpr int DUAL_THREADS = (1 + 1 + DUAL_EPI_WARPS) * 32;
+__host__ __device__ constexpr int dual_producer_warps(bool a4) { return a4 ? 4 : 1; }
+__host__ __device__ constexpr int dual_threads(bool a4) { return (dual_producer_warps(a4) + 1 + DUAL_EPI_WARPS) * 32; }
 
 struct alignas(64) DualMaps {
   CUtensorMap a;     // main activations {64 B, M rows, KT1}: box {64, TR, KC}
@@ -49,10 +50,11 @@ __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const CUtensorMap
                ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
 }
 
-template <int BN, bool WIDE>
-__global__ void __launch_bounds__(DUAL_THREADS, 1) conv_dual_kernel(const DualParams p, const __grid_constant__ DualMaps maps) {
+template <int BN, bool WIDE, bool A4>
+__global__ void __launch_bounds__(dual_threads(A4), 1) conv_dual_kernel(const DualParams p, const __grid_constant__ DualMaps maps) {
   constexpr int B_STAGE = BN * 64;
-  constexpr int MMA_WARP = 1, EPI_WARP0 = 2;
+  constexpr int NPW = dual_producer_warps(A4);
+  constexpr int MMA_WARP = NPW, EPI_WARP0 = NPW + 1;
   constexpr int CW = BN / 4;                 // columns per epilogue warp: 16 / 32
   constexpr int TMEM_COLS = 4 * BN;          // two accumulators x two buffers
   extern __shared__ uint8_t smem_raw[];
@@ -64,9 +66,11 @@ __global__ void __launch_bounds__(DUAL_THREADS, 1) conv_dual_kernel(const DualPa
   const uint32_t b_full = bar_base;
   auto afull = [&](int s) { return bar_base + 8u * (1 + s); };
   auto aempty = [&](int s) { return bar_base + 8u * (1 + DUAL_MAX_STAGES + s); };
-  auto tfull = [&](int b) { return bar_base + 8u * (1 + 2 * DUAL_MAX_STAGES + b); };
-  auto tempty = [&](int b) { return bar_base + 8u * (3 + 2 * DUAL_MAX_STAGES + b); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_bar + 8 * (5 + 2 * DUAL_MAX_STAGES));
+  auto kfull = [&](int s) { return bar_base + 8u * (1 + 2 * DUAL_MAX_STAGES + s); };    // A4: packed stage landed
+  auto kempty = [&](int s) { return bar_base + 8u * (1 + 3 * DUAL_MAX_STAGES + s); };
+  auto tfull = [&](int b) { return bar_base + 8u * (1 + 4 * DUAL_MAX_STAGES + b); };
+  auto tempty = [&](int b) { return bar_base + 8u * (3 + 4 * DUAL_MAX_STAGES + b); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_bar + 8 * (5 + 4 * DUAL_MAX_STAGES));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nt = blockIdx.x % p.n_tiles, slot = blockIdx.x / p.n_tiles;
@@ -77,8 +81,10 @@ __global__ void __launch_bounds__(DUAL_THREADS, 1) conv_dual_kernel(const DualPa
   if (tid == 0) {
     mbar_init(b_full, 1);
     for (int s = 0; s < DUAL_MAX_STAGES; ++s) {
-      mbar_init(afull(s), 1);
+      mbar_init(afull(s), A4 ? 4 : 1);        // A4: one arrival per converter warp
       mbar_init(aempty(s), 1);
+      mbar_init(kfull(s), 1);
+      mbar_init(kempty(s), 4);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull(b), 1);
@@ -94,9 +100,9 @@ __global__ void __launch_bounds__(DUAL_THREADS, 1) conv_dual_kernel(const DualPa
 
   asm volatile("griddepcontrol.launch_dependents;");
 
-  if (warp == 0) {
-    // =============================================================================== producer
-    if (elect_one()) {
+  if (warp < NPW) {
+    // =============================================================================== producer (+ A4 converters)
+    if (warp == 0 && elect_one()) {
       mbar_arrive_expect_tx(b_full, (uint32_t)KT * B_STAGE);      // plan-time data: before waiting for the previous kernel
       for (int i = 0; i < p.w1_boxes; ++i)
         tma_load_3d(smem_base + (uint32_t)(i * p.w1_box_kt) * B_STAGE, &maps.w1, 0, n0, i * p.w1_box_kt, b_full);
@@ -104,25 +110,86 @@ __global__ void __launch_bounds__(DUAL_THREADS, 1) conv_dual_kernel(const DualPa
         tma_load_3d(smem_base + (uint32_t)(p.KT1 + i * p.w2_box_kt) * B_STAGE, &maps.w2, 0, n0, i * p.w2_box_kt, b_full);
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (elect_one()) {
-      const uint32_t stage_bytes = (uint32_t)p.KC * p.TR * 64;
-      const uint32_t stage_alloc = (uint32_t)p.KC * 128 * 64;
-      uint32_t s = 0, ph = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int m0 = (slot + t * p.ctas_per_n) * p.TR;
-        for (int k0 = 0; k0 < p.KT1; k0 += p.KC) {
-          mbar_wait_small(aempty(s), ph ^ 1);
-          mbar_arrive_expect_tx(afull(s), stage_bytes);
-          tma_load_3d(smem_base + p.off_a + s * stage_alloc, &maps.a, 0, m0, k0, afull(s));
-          if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1; }
-        }
+    const uint32_t stage_bytes = (uint32_t)p.KC * p.TR * (A4 ? 32 : 64);
+    const uint32_t stage_alloc = (uint32_t)p.KC * 128 * 64, packed_alloc = (uint32_t)p.KC * 128 * 32;
+    const int S1 = p.KT1 / p.KC, S2 = p.KT2 / p.KC;               // stages per tile: main conv, identity conv
+    // stage j of tile t: j < S1 -> main conv k-tiles j * KC ..., else identity conv k-tiles (j - S1) * KC ...
+    auto load_stage = [&](int t, int j, uint32_t dst, uint32_t bar) {
+      const int m0 = (slot + t * p.ctas_per_n) * p.TR;
+      if (j < S1) {
+        tma_load_3d(dst, &maps.a, 0, m0, j * p.KC, bar);
+      } else if (p.strided) {
         const int img0 = m0 / p.HoWo, y0 = (m0 - img0 * p.HoWo) / p.Wo;
-        for (int k0 = 0; k0 < p.KT2; k0 += p.KC) {
-          mbar_wait_small(aempty(s), ph ^ 1);
-          mbar_arrive_expect_tx(afull(s), stage_bytes);
-          if (p.strided) tma_load_5d(smem_base + p.off_a + s * stage_alloc, &maps.a2, 0, 0, y0 * p.stride2, img0, k0, afull(s));
-          else tma_load_3d(smem_base + p.off_a + s * stage_alloc, &maps.a2, 0, m0, k0, afull(s));
-          if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1; }
+        tma_load_5d(dst, &maps.a2, 0, 0, y0 * p.stride2, img0, (j - S1) * p.KC, bar);
+      } else {
+        tma_load_3d(dst, &maps.a2, 0, m0, (j - S1) * p.KC, bar);
+      }
+    };
+    if constexpr (!A4) {
+      if (elect_one()) {
+        uint32_t s = 0, ph = 0;
+        for (int t = 0; t < my_tiles; ++t)
+          for (int j = 0; j < S1 + S2; ++j) {
+            mbar_wait_small(aempty(s), ph ^ 1);
+            mbar_arrive_expect_tx(afull(s), stage_bytes);
+            load_stage(t, j, smem_base + p.off_a + s * stage_alloc, afull(s));
+            if (++s == (uint32_t)p.NS) { s = 0; ph ^= 1; }
+          }
+      }
+    } else {
+      // packed 4-bit rows: TMA -> packed stage ([k-tile][TR rows][32 B], SWIZZLE_32B) -> these 128 threads expand every row to int8 in
+      // the K order the permuted weights expect -> [k-tile][TR rows][64 B], SWIZZLE_64B (swizzle phase = absolute row kt * TR + r)
+      const int spt = S1 + S2, total_g = my_tiles * spt;
+      auto issue = [&](int g) {            // one elected lane of warp 0
+        const int t = g / spt, j = g - t * spt, ks = g % p.NS;
+        mbar_wait_small(kempty(ks), ((g / p.NS) & 1) ^ 1);
+        mbar_arrive_expect_tx(kfull(ks), stage_bytes);
+        load_stage(t, j, smem_base + p.off_packed + ks * packed_alloc, kfull(ks));
+      };
+      if (warp == 0) {
+        for (int g = 0; g < p.NS - 1 && g < total_g; ++g)
+          if (elect_one()) issue(g);
+        __syncwarp();
+      }
+      for (int g = 0; g < total_g; ++g) {
+        if (warp == 0) {
+          if (g + p.NS - 1 < total_g && elect_one()) issue(g + p.NS - 1);
+          __syncwarp();
+        }
+        const int s = g % p.NS;
+        mbar_wait_small(kfull(s), (g / p.NS) & 1);
+        mbar_wait_small(aempty(s), ((g / p.NS) & 1) ^ 1);
+        const uint8_t* src = smem + p.off_packed + s * packed_alloc;
+        uint8_t* dst = smem + p.off_a + s * stage_alloc;
+        if (tid < p.TR) {
+          uint4 wv[4][2];
+#pragma unroll
+          for (int kt = 0; kt < 4; ++kt)
+            if (kt < p.KC) {
+              const int pr = kt * p.TR + tid;
+#pragma unroll
+              for (int blk = 0; blk < 2; ++blk) wv[kt][blk] = *reinterpret_cast<const uint4*>(src + pr * 32 + ((blk ^ ((pr >> 2) & 1)) << 4));
+            }
+#pragma unroll
+          for (int kt = 0; kt < 4; ++kt)
+            if (kt < p.KC) {
+              const int pr = kt * p.TR + tid;
+              const uint32_t a_sw = (pr >> 1) & 3;
+#pragma unroll
+              for (int blk = 0; blk < 2; ++blk) {
+                const uint4 v = wv[kt][blk];
+                const uint4 lo = make_uint4(v.x & 0x0F0F0F0Fu, v.y & 0x0F0F0F0Fu, v.z & 0x0F0F0F0Fu, v.w & 0x0F0F0F0Fu);
+                const uint4 hi = make_uint4((v.x >> 4) & 0x0F0F0F0Fu, (v.y >> 4) & 0x0F0F0F0Fu, (v.z >> 4) & 0x0F0F0F0Fu, (v.w >> 4) & 0x0F0F0F0Fu);
+                *reinterpret_cast<uint4*>(dst + pr * 64 + (((2 * blk) ^ a_sw) << 4)) = lo;
+                *reinterpret_cast<uint4*>(dst + pr * 64 + (((2 * blk + 1) ^ a_sw) << 4)) = hi;
+              }
+            }
+        }
+        fence_proxy_async();             // generic-proxy writes -> tcgen05.mma (async proxy) reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(afull(s));
+          mbar_arrive(kempty(s));
         }
       }
     }
@@ -130,7 +197,7 @@ __global__ void __launch_bounds__(DUAL_THREADS, 1) conv_dual_kernel(const DualPa
     // =============================================================================== MMA issuer
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_i8(128, BN, true);
+      const uint32_t idesc = umma_idesc_i8(128, BN, !A4);          // packed 4-bit activations are unsigned
       const uint32_t desc_hi = (uint32_t)(umma_desc_sw64(0) >> 32);
       constexpr uint32_t BU = B_STAGE >> 4;
       const uint32_t AU = (uint32_t)p.TR * 4u;                    // one activation k-tile (TR rows x 64 B) in descriptor units

@@ -177,6 +177,18 @@ def stem_conv(x, w, chan, clamp, out, n, hh, ww):
     _count("stem_conv", (n * ho * wo * 64 * 147, n * hh * ww * 3 + 64 * 224 + 1024 + n * ho * wo * 64 * 2) if ev is not None else None, ev)
 
 
+def stem_pool(x, w256, chan, clamp, n, hh, ww, y_bits, y, low_bits, low_me, low_clamp, out_low):
+    """Fused stem (conv 7x7/2 + max-pool 3x3/2 + 16-bit requant + ReLU + low-bit copy) in one kernel; raises HawqError(ERR_UNSUPPORTED)
+    for shapes / ratios outside it (callers then use stem_conv + maxpool_requant, same integers)."""
+    h, s = _ctx(x)
+    ev = _begin()
+    _lib.check(_lib.load().hawq_stem_pool_i8(h, n, hh, ww, _p(x), _p(w256), _p(chan), clamp[0], clamp[1], y_bits, _p(y), low_bits, low_me[0],
+                                             low_me[1], low_clamp[0], low_clamp[1], _p(out_low), s))
+    ho, wo = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+    po, qo = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
+    _count("stem_tc", (n * ho * wo * 64 * 147, n * hh * ww * 3 + 64 * 256 + 1024 + n * po * qo * 64 * (y_bits + low_bits) // 8) if ev is not None else None, ev)
+
+
 def maxpool_requant(x, n, hh, ww, c, y_bits, y, low_bits, low_me, low_clamp, out_low):
     h, s = _ctx(x)
     ev = _begin()

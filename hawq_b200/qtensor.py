@@ -258,10 +258,12 @@ def _conv_cache(mod, a_sf, a_bits, device):
         w = w_int.detach().to("cpu").permute(0, 2, 3, 1).contiguous().to(torch.int8)      # OHWI
         bias = (b_int.detach().to("cpu").to(torch.int64).numpy() if b_int is not None else np.zeros(cout, dtype=np.int64))
         stem = (cin == 3 and kh == 7 and conv.stride[0] == 2 and conv.padding[0] == 3 and cout == 64)
+        w256 = None
         if stem:
-            wp = torch.zeros((cout, 7, 8, 4), dtype=torch.int8)
-            wp[:, :, :7, :3] = w
-            w = wp
+            wp = torch.zeros((cout, 8, 8, 4), dtype=torch.int8)       # kernel rows 7 -> 8, taps 7 -> 8, channels 3 -> 4 (zeros)
+            wp[:, :7, :7, :3] = w
+            w256 = wp.to(device)                                      # fused tcgen05 stem: K = 256
+            w = wp[:, :7].contiguous()                                # two-kernel path: K = 224
         else:
             if cin % 64 != 0 or cout % 64 != 0:
                 raise NotImplementedError("hawq_b200 convolutions need Cin and Cout multiples of 64 (got %d, %d)" % (cin, cout))
@@ -269,7 +271,7 @@ def _conv_cache(mod, a_sf, a_bits, device):
                 ops.permute_weights_for_i4(w)
         tiled = (not stem) and torch.device(device).type == "cuda"
         ent = dict(w=ops.upload_weights(w, device) if tiled else w.to(device), w_layout=1 if tiled else 0, w_sf=w_sf, bias=bias, cout=cout, cin=cin, k=kh, stride=conv.stride[0],
-                   pad=conv.padding[0], stem=stem, chan={})
+                   pad=conv.padding[0], stem=stem, chan={}, w256=w256)
     c[key] = ent
     return ent
 
@@ -475,8 +477,6 @@ def _launch_stem(st, low_act, device):
     nb, _, hh, ww = src.shape
     ho, wo = (hh + 6 - 7) // 2 + 1, (ww + 6 - 7) // 2 + 1
     lo, hi = _act_clamp(act)
-    t16 = torch.empty(nb * ho * wo * 64, dtype=torch.int16, device=device)
-    ops.stem_conv(src.data, ent["w"], chan, (lo, hi), t16, nb, hh, ww)
     po, qo = (ho + 2 - 3) // 2 + 1, (wo + 2 - 3) // 2 + 1
     numel = nb * po * qo * 64
     y_bits = config.residual_bits
@@ -489,7 +489,18 @@ def _launch_stem(st, low_act, device):
         low_bits, low_me, low_clamp = low_act.activation_bit, (lm[0], le[0]), _act_clamp(low_act)
         low = _alloc(device, numel, low_bits)
         low_node = Node("int", (nb, 64, po, qo), data=low, bits=low_bits, signed=(low_act.quant_mode == "symmetric"))
-    ops.maxpool_requant(t16, nb, ho, wo, 64, y_bits, y, low_bits, low_me, low_clamp, low)
+    fused = False
+    if config.fast_kernels and min(e) >= 31 and (low_bits == 0 or low_me[0] == 0 or 31 <= low_me[1] <= 51):
+        try:                    # one kernel: convolution, pool, requantisation, low-bit copy (the int16 tensor never exists)
+            ops.stem_pool(src.data, ent["w256"], chan, (lo, hi), nb, hh, ww, y_bits, y, low_bits, low_me, low_clamp, low)
+            fused = True
+        except HawqError as err:
+            if err.code != ERR_UNSUPPORTED:
+                raise
+    if not fused:
+        t16 = torch.empty(nb * ho * wo * 64, dtype=torch.int16, device=device)
+        ops.stem_conv(src.data, ent["w"], chan, (lo, hi), t16, nb, hh, ww)
+        ops.maxpool_requant(t16, nb, ho, wo, 64, y_bits, y, low_bits, low_me, low_clamp, low)
     st.shape = (nb, 64, po, qo)
     st.become_int(y, y_bits, signed=(y_bits == 32))
     return low_node

@@ -161,6 +161,14 @@ int hawq_linear_i8(hawq_handle* h, int32_t N, int32_t K, int32_t Cout, int32_t C
 int hawq_stem_conv_i8(hawq_handle* h, int32_t N, int32_t H, int32_t W, const int8_t* x, const int8_t* w,
                       const hawq_chan* chan, int32_t clamp_lo, int32_t clamp_hi, int16_t* out, void* stream);
 
+/* Fused stem (tcgen05): quant_init_convbn (7x7 stride 2 pad 3, Cin = 3 -> 64) + nn.MaxPool2d(3, 2, 1) + quant_act_int32 (16-bit dyadic
+ * requant, clamp) + ReLU, and optionally the first unit's low-bit quant_act (q_resnet.py:117-122, :234) in one kernel; the int16
+ * convolution output never reaches HBM.  w256 = int8 [64][8][8][4] (kernel rows padded 7 -> 8, taps 7 -> 8, channels 3 -> 4, zeros
+ * in the padding).  y = pooled residual stream [N][Hp][Wp][64] as uint16 (y_bits 16) or int32 (32).  Preconditions: every ratio
+ * <= 1, W % 4 == 0, W <= 256; otherwise HAWQ_ERR_UNSUPPORTED (use hawq_stem_conv_i8 + hawq_maxpool_requant: same integers). */
+int hawq_stem_pool_i8(hawq_handle* h, int32_t N, int32_t H, int32_t W, const int8_t* x, const int8_t* w256, const hawq_chan* chan,
+                      int32_t clamp_lo, int32_t clamp_hi, int32_t y_bits, void* y, int32_t low_bits, uint32_t low_m, int32_t low_e,
+                      int32_t low_lo, int32_t low_hi, void* out_low, void* stream);
 /* nn.MaxPool2d(3,2,1) (q_resnet.py:119) on the int16 stem output + the first unit's quant_act (case 0, scalar m,e).
  * y: residual stream (y_bits 16 -> uint16, 32 -> int32); out_low: int8 / packed u4 (low_bits 8 / 4, 0 = none). */
 int hawq_maxpool_requant(hawq_handle* h, int32_t N, int32_t H, int32_t W, int32_t C, const int16_t* x,
@@ -213,13 +221,15 @@ int hawq_retile_weights(hawq_handle* h, const int8_t* w_ohwi, int32_t Cout, int6
 /* debug: number of hawq_conv2d launches so far that went to kernel family 0 = conv_tc (generic tcgen05 implicit GEMM),
  * 1 = conv_halo (3x3 stride-1, A operand read in place), 2 = conv_halo launches that needed the 2-D weight-map fallback,
  * 3 = conv1x1 (1x1 stride-1, stationary weights), 4 = conv_dual (resize-unit tail, stationary weights), 5 = resize-unit tails
- * on conv_tc;
+ * on conv_tc, 6 = fused tcgen05 stem;
  * -1 for an unknown family.  Lets tests assert which kernel ran. */
 int64_t hawq_debug_kernel_count(int32_t family);
 /* debug: with HAWQ_B200_HALO_TRACE=1 in the environment every conv_halo launch records clock64 stamps of CTA 0
  * ([3 roles: producer, MMA issuer, epilogue][64 steps][4 events]); this copies the last launch's buffer to the host (synchronises
  * the device) and returns the number of int64 values written.  Not for production use. */
 int32_t hawq_debug_halo_trace(int64_t* host_out, int32_t n);
+/* same for the last conv1x1 launch: [4 roles: producer / converter, MMA issuer, epilogue, residual loader][48 tiles][4 events] */
+int32_t hawq_debug_c1_trace(int64_t* host_out, int32_t n);
 /* workspace query kept for ABI completeness: this build needs no scratch beyond caller tensors */
 int64_t hawq_workspace_bytes(const hawq_conv_desc* d, const hawq_epilogue_desc* ep);
 

@@ -150,6 +150,15 @@ def stem_conv(x, w, chan, clamp, out, n, hh, ww):
     encode_into(out, q, 16)
 
 
+def stem_pool(x, w256, chan, clamp, n, hh, ww, y_bits, y, low_bits, low_me, low_clamp, out_low):
+    """hawq_stem_pool_i8 == hawq_stem_conv_i8 followed by hawq_maxpool_requant."""
+    w = w256.detach().cpu().reshape(64, 8, 8, 4)[:, :7].contiguous()
+    ho, wo = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+    t16 = torch.zeros(n * ho * wo * 64, dtype=torch.int16)
+    stem_conv(x, w, chan, clamp, t16, n, hh, ww)
+    maxpool_requant(t16, n, ho, wo, 64, y_bits, y, low_bits, low_me, low_clamp, out_low)
+
+
 def maxpool_requant(x, n, hh, ww, c, y_bits, y, low_bits, low_me, low_clamp, out_low):
     xa = decode(x, 16, True).reshape(n, hh, ww, c)
     p = ir.maxpool_3x3_s2_p1(xa)
@@ -229,7 +238,7 @@ def install_cpu_backend(monkeypatch):
     """Route hawq_b200.ops launchers to this model (CPU tensors).  Test-only."""
     from hawq_b200 import ops
     status["flags"] = 0
-    for name, fn in dict(conv2d=conv2d, conv2d_dual=conv2d_dual, linear=linear, stem_conv=stem_conv, maxpool_requant=maxpool_requant,
+    for name, fn in dict(conv2d=conv2d, conv2d_dual=conv2d_dual, linear=linear, stem_conv=stem_conv, stem_pool=stem_pool, maxpool_requant=maxpool_requant,
                          avgpool_requant=avgpool_requant, quantize_input=quantize_input, quantize_input_u8=quantize_input_u8, requant=requant,
                          add_requant=add_requant, dequant=dequant, pack_i4=pack_i4_op, unpack_i4=unpack_i4_op).items():
         monkeypatch.setattr(ops, name, fn)

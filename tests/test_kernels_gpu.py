@@ -542,23 +542,27 @@ DUALK_GEOMS = [
 
 
 @pytest.mark.parametrize("flag", [1, 2])
+@pytest.mark.parametrize("a_bits", [8, 4])
 @pytest.mark.parametrize("geom", DUALK_GEOMS)
-def test_conv_dual_stationary_weights(geom, flag):
-    """int8 resize-unit tails take conv_dual.cuh (counter 4): bit-exact vs RAW_I32 identity conv + res_kind-1 RESIDUAL conv of the ABI model."""
+def test_conv_dual_stationary_weights(geom, a_bits, flag):
+    """Resize-unit tails take conv_dual.cuh (counter 4): bit-exact vs RAW_I32 identity conv + res_kind-1 RESIDUAL conv of the ABI model."""
     from hawq_b200 import _lib
     n, ho, wo, cin, cin2, cout, s2 = geom
-    r = rng(31337 + sum(v * (i + 3) for i, v in enumerate(geom)) * 4 + flag)
+    r = rng(31337 + sum(v * (i + 3) for i, v in enumerate(geom)) * 4 + flag + a_bits)
     h2, w2 = ho * s2, wo * s2
     numel = n * ho * wo * cout
-    x = rand_act(r, n * ho * wo * cin, 8)
-    x2 = rand_act(r, n * h2 * w2 * cin2, 8)
+    x = rand_act(r, n * ho * wo * cin, a_bits)
+    x2 = rand_act(r, n * h2 * w2 * cin2, a_bits)
     wt = torch.from_numpy(r.randint(-8, 8, size=(cout, 1, 1, cin)).astype(np.int8))
     wt2 = torch.from_numpy(r.randint(-8, 8, size=(cout, 1, 1, cin2)).astype(np.int8))
+    if a_bits == 4:
+        ops.permute_weights_for_i4(wt)
+        ops.permute_weights_for_i4(wt2)
     hi = 0.9 if flag == 1 else 30.0
     chan = make_chan(r, cout, bias_mag=3000, ratio_lo=1e-2, ratio_hi=hi)
     chan2 = make_chan(r, cout, bias_mag=3000, ratio_lo=1e-2, ratio_hi=hi)
-    d = ops.conv_desc(n, ho, wo, cin, cout, 1, 1, 1, 0, 8, 1)
-    d2 = ops.conv_desc(n, h2, w2, cin2, cout, 1, 1, s2, 0, 8, 1)
+    d = ops.conv_desc(n, ho, wo, cin, cout, 1, 1, 1, 0, a_bits, 1)
+    d2 = ops.conv_desc(n, h2, w2, cin2, cout, 1, 1, s2, 0, a_bits, 1)
     wg, wg2 = ops.upload_weights(wt, DEV), ops.upload_weights(wt2, DEV)
     for low_bits in (8, 4, 0):
         ep = ops.epilogue(EPI_RESIDUAL, relu=1, res_kind=1, res_bits=32, y_bits=16, low_bits=low_bits, low_me=dyadic(0.003),
@@ -572,5 +576,28 @@ def test_conv_dual_stationary_weights(geom, flag):
         assert _lib.load().hawq_debug_kernel_count(4) == before + 1, "conv_dual did not take this launch"
         assert ops.get_status(0) & 6 == 0
         for a, b, k_ in zip(cs, gs, keys):
-            assert torch.equal(a, b), (geom, flag, low_bits, k_)
+            assert torch.equal(a, b), (geom, a_bits, flag, low_bits, k_)
     ops.reset_status(0)
+
+
+@pytest.mark.parametrize("shape", [(2, 224, 224), (3, 64, 48), (1, 32, 256), (5, 20, 12), (2, 58, 36)])
+def test_stem_pool_fused(shape):
+    """hawq_stem_pool_i8 (tcgen05 stem: conv + max-pool + 16-bit requant + ReLU + low-bit copy) == hawq_stem_conv_i8 followed by
+    hawq_maxpool_requant of the ABI model, for the uint16 and the int32 stream, 8 / 4-bit and no low copy, bands that end inside the image."""
+    n, h, w = shape
+    r = rng(n * h + 3 * w)
+    x = torch.from_numpy(r.randint(-128, 128, size=n * h * w * 3).astype(np.int8))
+    wt = torch.zeros((64, 8, 8, 4), dtype=torch.int8)
+    wt[:, :7, :7, :3] = torch.from_numpy(r.randint(-128, 128, size=(64, 7, 7, 3)).astype(np.int8))
+    chan = make_chan(r, 64, ratio_lo=0.05, ratio_hi=0.8)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    po, qo = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
+    for y_bits, low_bits, clamp in [(16, 8, (-32768, 32767)), (32, 4, (-32768, 32767)), (16, 0, (-3000, 20000)), (16, 4, (-32768, 32767))]:
+        args = dict(x=x, w256=wt, chan=chan, clamp=clamp, n=n, hh=h, ww=w, y_bits=y_bits, y=out_buf(n * po * qo * 64, y_bits),
+                    low_bits=low_bits, low_me=dyadic(0.003), low_clamp=(0, 15) if low_bits == 4 else (-128, 127),
+                    out_low=out_buf(n * po * qo * 64, low_bits) if low_bits else None)
+        keys = ["y"] + (["out_low"] if low_bits else [])
+        cs, gs = run_both("stem_pool", args, keys)
+        for a, b, k_ in zip(cs, gs, keys):
+            assert torch.equal(a, b), (shape, y_bits, low_bits, k_, int((a != b).sum()))
+    assert ops.get_status(0) == 0

@@ -15,6 +15,9 @@ for what in "$@"; do
     dualk)
       timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "dual" > gpurun_out/pytest_dual.log 2>&1
       echo "dual exit $?"; tail -15 gpurun_out/pytest_dual.log;;
+    stem)
+      timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "stem" > gpurun_out/pytest_stem.log 2>&1
+      echo "stem exit $?"; tail -15 gpurun_out/pytest_stem.log;;
     halo)
       timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -p no:cacheprovider -k "halo" > gpurun_out/pytest_halo.log 2>&1
       echo "halo exit $?"; tail -15 gpurun_out/pytest_halo.log;;
