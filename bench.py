@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--residual-bits", type=int, default=16)
+    ap.add_argument("--a4-storage", default="byte", choices=["byte", "packed"],
+                    help="HBM container of 4-bit activations: one value per byte (default, consumed directly by the int8 tensor-core kernels) or packed nibbles expanded on chip")
     ap.add_argument("--detail", default="", help="write per-layer timings to this JSON file")
     return ap.parse_args()
 
@@ -220,6 +222,8 @@ def run_ours(a):
     build_library()
 
     B = a.batch
+    from hawq_b200 import qtensor as _qt
+    _qt.config.a4_container = 4 if a.a4_storage == "packed" else 8
     q = hb.build_synthetic_qresnet(a.arch, a.scheme, calib_batch=4, calib_seed=0)
     s_in = float(q.quant_input.current_scale())
     # synthetic int8 images: POOL different batches per rank so consecutive steps never see the same input
@@ -303,12 +307,14 @@ def run_ours(a):
         macs = MACS_PER_IMAGE.get(a.arch, 0.0)
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int8" if a.scheme == "uniform8" else ("int4 storage / int8 MMA" if a.scheme == "uniform4" else "mixed int4/int8"),
+                "dtype": "int8" if a.scheme == "uniform8" else (("int4 values (%s in HBM) / int8 MMA" if a.scheme == "uniform4" else "mixed int4 (%s in HBM) and int8 / int8 MMA")
+                                                                % ("packed nibbles" if a.a4_storage == "packed" else "one per byte")),
                 "data": "synthetic",
                 "config": dict(workload_config(a, world, detail),
                                l2=("per-step working set (%.1f GB of activations) exceeds the 126 MB L2; %d input batches rotate" % (detail["act_bytes"] / 1e9, POOL)) if detail and detail["act_bytes"] > 2.5e8
                                else "%d input batches rotate; at this batch size the per-step working set is L2-resident (latency-bound regime)" % POOL,
                                residual_stream="uint%d" % a.residual_bits if a.residual_bits == 16 else "int32", cuda_graph=True,
+                               a4_storage=a.a4_storage,
                                overflow_flag_seen=bool(flag & 1)),
                 "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(host_pool[0].numel()),
                         "d2h_bytes_per_step": int(B * 1000 * 4 + 4), "ms_per_step": ms_e2e / a.steps,

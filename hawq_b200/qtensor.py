@@ -37,6 +37,11 @@ class EngineConfig(threading.local):
     residual_bits = 32
     fast_kernels = True
     checked = False
+    # HBM container of 4-bit activations: 8 = one value per byte (the int8 kernels consume them directly: Blackwell has no int4 MMA,
+    # so packed nibbles must be expanded on chip before every use), 4 = packed nibbles (half the bytes of those tensors, expansion by
+    # converter warps).  Same integers either way; today the byte container is faster on every ResNet layer (profiles/r02), the
+    # packed one is kept for bandwidth-bound deployments and is what the kernel tests exercise with a_bits = 4.
+    a4_container = 4 if os.environ.get("HAWQ_B200_A4_STORAGE", "byte") == "packed" else 8
     dual = os.environ.get("HAWQ_B200_DUAL", "1") != "0"   # resize units: identity conv + last conv in one kernel (uint16 stream only)
 
 
@@ -184,6 +189,17 @@ def _alloc(device, numel, bits):
 
 def _act_clamp(act):
     return qmath.clamp_range(act.activation_bit, act.quant_mode)
+
+
+def _store_bits(act):
+    """Bits per value of `act`'s output in HBM (see EngineConfig.a4_container)."""
+    b = act.activation_bit
+    return config.a4_container if b == 4 else b
+
+
+def _store_signed(act):
+    """Whether the stored integers may be read as signed bytes: symmetric activations, and 4-bit values in byte containers (0..15)."""
+    return act.quant_mode == "symmetric" or (act.activation_bit == 4 and _store_bits(act) == 8)
 
 
 def _frozen_scale(act):
@@ -370,13 +386,13 @@ def _conv_case0(n, act, device):
     m, e = _dyadic(act, n.a_sf, ent["w_sf"], "case0")
     chan = _chan_tensor(ent, _act_tag("c0", act), m, e, device)
     nb, _, _, ho, wo = _conv_out_hw(n, ent)
-    bits = act.activation_bit
+    bits = _store_bits(act)
     lo, hi = _act_clamp(act)
     out = _alloc(device, nb * ho * wo * ent["cout"], bits)
     ep = ops.epilogue(EPI_REQUANT, relu=n.relu, out_bits=bits, clamp=(lo, hi),
                       flags=_ratio_flags((m, e)))
     _launch_conv(n, ent, ep, chan, device, out=out)
-    return Node("int", (nb, ent["cout"], ho, wo), data=out, bits=bits, signed=(act.quant_mode == "symmetric"))
+    return Node("int", (nb, ent["cout"], ho, wo), data=out, bits=bits, signed=_store_signed(act))
 
 
 def _conv_raw(n, device):
@@ -434,11 +450,10 @@ def _launch_residual(r, low_act, device):
         lscale = _frozen_scale(low_act)
         lm, le = _dyadic(low_act, _frozen_scale(act), _ones(), "case0")
         lo, hi = _act_clamp(low_act)
-        low = _alloc(device, numel, low_act.activation_bit)
-        kw = dict(low_bits=low_act.activation_bit, low_me=(lm[0], le[0]), low_clamp=(lo, hi))
+        low = _alloc(device, numel, _store_bits(low_act))
+        kw = dict(low_bits=_store_bits(low_act), low_me=(lm[0], le[0]), low_clamp=(lo, hi))
         pairs.append((lm[0], le[0]))
-        low_node = Node("int", (nb, ent["cout"], ho, wo), data=low, bits=low_act.activation_bit,
-                        signed=(low_act.quant_mode == "symmetric"))
+        low_node = Node("int", (nb, ent["cout"], ho, wo), data=low, bits=_store_bits(low_act), signed=_store_signed(low_act))
     ep = ops.epilogue(EPI_RESIDUAL, relu=r.relu, res_kind=res_kind, res_bits=res_bits, res_me=res_me, y_bits=y_bits,
                       flags=_ratio_flags(*pairs), **kw)
     if dual is not None and ep.flags == 0:       # no ratio promise (saturating generic kernels): two launches
@@ -486,9 +501,9 @@ def _launch_stem(st, low_act, device):
     if low_act is not None:
         _frozen_scale(low_act)
         lm, le = _dyadic(low_act, _frozen_scale(act), _ones(), "case0")
-        low_bits, low_me, low_clamp = low_act.activation_bit, (lm[0], le[0]), _act_clamp(low_act)
+        low_bits, low_me, low_clamp = _store_bits(low_act), (lm[0], le[0]), _act_clamp(low_act)
         low = _alloc(device, numel, low_bits)
-        low_node = Node("int", (nb, 64, po, qo), data=low, bits=low_bits, signed=(low_act.quant_mode == "symmetric"))
+        low_node = Node("int", (nb, 64, po, qo), data=low, bits=low_bits, signed=_store_signed(low_act))
     fused = False
     if config.fast_kernels and min(e) >= 31 and (low_bits == 0 or low_me[0] == 0 or 31 <= low_me[1] <= 51):
         try:                    # one kernel: convolution, pool, requantisation, low-bit copy (the int16 tensor never exists)
@@ -588,10 +603,9 @@ def act_forward(act, x, a_sf, w_sf, identity, id_sf, id_w_sf):
         chan = ops.make_chan([0] * len(m), m, e).to(dev)
         rows = int(np.prod(n.shape)) // c
         lo, hi = _act_clamp(act)
-        out = _alloc(dev, rows * c, act.activation_bit)
-        ops.requant(n.data, rows, c, n.bits, chan, 1 if per_ch else 0, False, act.activation_bit, (lo, hi), out)
-        return (IntActivation(Node("int", n.shape, data=out, bits=act.activation_bit,
-                                   signed=(act.quant_mode == "symmetric")), dev), scale)
+        out = _alloc(dev, rows * c, _store_bits(act))
+        ops.requant(n.data, rows, c, n.bits, chan, 1 if per_ch else 0, False, _store_bits(act), (lo, hi), out)
+        return (IntActivation(Node("int", n.shape, data=out, bits=_store_bits(act), signed=_store_signed(act)), dev), scale)
     raise NotImplementedError("QuantAct on a pending %s" % n.kind)
 
 

@@ -28,11 +28,13 @@ def _hook_outputs(q):
     return rec, hooks
 
 
-@pytest.mark.parametrize("arch,scheme,res_bits", [("resnet18", "uniform8", 32), ("resnet18", "uniform4", 16),
-                                                  ("resnet18", "bops_0.5", 32), ("resnet50", "bops_0.5", 16),
-                                                  ("resnet101", "uniform4", 16)])
-def test_frozen_graph_matches_golden(monkeypatch, arch, scheme, res_bits):
+@pytest.mark.parametrize("arch,scheme,res_bits,a4_container", [("resnet18", "uniform8", 32, 8), ("resnet18", "uniform4", 16, 8),
+                                                               ("resnet18", "uniform4", 32, 4), ("resnet18", "bops_0.5", 32, 8),
+                                                               ("resnet50", "bops_0.5", 16, 4), ("resnet101", "uniform4", 16, 8)])
+def test_frozen_graph_matches_golden(monkeypatch, arch, scheme, res_bits, a4_container):
+    """a4_container: 4-bit activations stored one per byte (default) or as packed nibbles - same integers either way."""
     abi_model.install_cpu_backend(monkeypatch)
+    monkeypatch.setattr(qtensor.config, "a4_container", a4_container)
     logits_g, meta = load_net_golden(arch, scheme)
     x = synthetic_batch(*meta["input"])
     # oracle trace (full tensors), itself pinned to the golden checksums

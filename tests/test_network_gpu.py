@@ -69,10 +69,14 @@ def test_every_activation_matches_oracle(arch, scheme):
     assert np.array_equal(out.cpu().numpy(), logits_g)
 
 
-@pytest.mark.parametrize("arch,scheme", [("resnet18", "uniform8"), ("resnet50", "uniform8"), ("resnet50", "uniform4"), ("resnet50", "bops_0.5")])
-def test_compiled_graph_int8_input_and_batch_invariance(arch, scheme):
+@pytest.mark.parametrize("arch,scheme,a4_container", [("resnet18", "uniform8", 8), ("resnet50", "uniform8", 8), ("resnet50", "uniform4", 8),
+                                                      ("resnet50", "uniform4", 4), ("resnet50", "bops_0.5", 8), ("resnet50", "bops_0.5", 4),
+                                                      ("resnet18", "uniform4", 4)])
+def test_compiled_graph_int8_input_and_batch_invariance(arch, scheme, a4_container, monkeypatch):
     """CUDA-graph engine on int8 NHWC input at a larger batch: the first two images are the golden inputs, so their
-    logits must equal the golden logits whatever else is in the batch (size-independent property); replays are idempotent."""
+    logits must equal the golden logits whatever else is in the batch (size-independent property); replays are idempotent.
+    a4_container: 4-bit activations one per byte (default) or as packed nibbles expanded on chip - same logits."""
+    monkeypatch.setattr(qtensor.config, "a4_container", a4_container)
     logits_g, meta = load_net_golden(arch, scheme)
     q = _model(arch, scheme, meta)
     B = 32
@@ -145,16 +149,17 @@ def test_compiled_graph_uint8_pixels_equal_the_torch_pipeline():
 
 
 # BASELINE.json configurations 1-4 at the batch sizes that are benchmarked (config 5 = config "resnet50 uniform4" per GPU)
-BENCH_CONFIGS = [("resnet18", "uniform8", 8), ("resnet18", "uniform4", 128), ("resnet50", "uniform8", 128),
-                 ("resnet50", "bops_0.5", 128), ("resnet50", "uniform4", 128), ("resnet50", "uniform8", 8)]
+BENCH_CONFIGS = [("resnet18", "uniform8", 8, 8), ("resnet18", "uniform4", 128, 8), ("resnet50", "uniform8", 128, 8),
+                 ("resnet50", "bops_0.5", 128, 8), ("resnet50", "uniform4", 128, 8), ("resnet50", "uniform4", 128, 4), ("resnet50", "uniform8", 8, 8)]
 
 
-@pytest.mark.parametrize("arch,scheme,batch", BENCH_CONFIGS)
-def test_benchmarked_configuration_matches_oracle_on_every_row(arch, scheme, batch):
+@pytest.mark.parametrize("arch,scheme,batch,a4_container", BENCH_CONFIGS)
+def test_benchmarked_configuration_matches_oracle_on_every_row(arch, scheme, batch, a4_container, monkeypatch):
     """The configuration bench.py times (CUDA graph, fused kernels, uint16 stream) at the benchmarked batch size against the
     oracle (the reference's fake-quant forward restated on the CPU, oracle/fakequant.py): ALL rows of the logits bit-equal, and the
     integers of the residual stream at the end of stage 1 and of the last stage (eager pass with the same kernels) equal too.
     Late tiles of the persistent kernels (many tiles per CTA, barrier phase flips, TMEM double buffering) are only reached at this size."""
+    monkeypatch.setattr(qtensor.config, "a4_container", a4_container)
     _, meta = load_net_golden(arch, scheme)
     x = synthetic_batch(batch, 11)
     fqm = build_fakequant(arch, scheme, meta)

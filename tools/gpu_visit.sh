@@ -32,10 +32,10 @@ for what in "$@"; do
       echo "pytest full exit $?"; tail -8 gpurun_out/pytest_gpu_full.log
       timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/smoke.log;;
     bench*)
-      IFS=: read -r _ arch scheme batch <<< "$what"
-      arch=${arch:-resnet50}; scheme=${scheme:-uniform8}; batch=${batch:-128}
-      tag=${arch}_${scheme}_b${batch}
-      timeout 600 python bench.py --arch $arch --scheme $scheme --batch $batch --steps ${STEPS:-50} --warmup 5 --no-cpu-baseline --detail gpurun_out/detail_$tag.json > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
+      IFS=: read -r _ arch scheme batch a4 <<< "$what"
+      arch=${arch:-resnet50}; scheme=${scheme:-uniform8}; batch=${batch:-128}; a4=${a4:-byte}
+      tag=${arch}_${scheme}_b${batch}; [[ $a4 == packed ]] && tag=${tag}_packed
+      timeout 600 python bench.py --arch $arch --scheme $scheme --batch $batch --a4-storage $a4 --steps ${STEPS:-50} --warmup 5 --no-cpu-baseline --detail gpurun_out/detail_$tag.json > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
       echo "bench $tag exit $?"; python - <<PY
 import json
 try:
