@@ -147,7 +147,8 @@ int launch_conv1x1(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_de
   if (M > 0x7fffff00ll) return 1;
   C1Plan plan;
   memset(&plan, 0, sizeof(plan));
-  if (!((d->Cout % 128 == 0 && plan_for(128, a4, is_res, KT, &plan)) || plan_for(64, a4, is_res, KT, &plan))) return 1;
+  static const bool narrow = [] { const char* v = getenv("HAWQ_B200_BN"); return v && atoi(v) == 64; }();   // experiment switch: 64-channel blocks
+  if (!((d->Cout % 128 == 0 && !narrow && plan_for(128, a4, is_res, KT, &plan)) || plan_for(64, a4, is_res, KT, &plan))) return 1;
   C1Params& p = plan.p;
   p.chan = chan; p.out = (uint8_t*)out; p.out_low = (uint8_t*)out_low; p.status = status;
   p.M = (int)M; p.Cout = d->Cout; p.KT = KT;

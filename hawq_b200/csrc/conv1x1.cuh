@@ -271,6 +271,20 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int row = quarter * 32 + lane;
     const double2* cst = sCst + cg * CW;
+    // CW == 16: the thread's 16 channel constants live in registers (bias folded into an integer add, ratio as a double) instead
+    // of one broadcast LDS.128 per value: a broadcast LDS.128 occupies the shared-memory pipe for 4 cycles per warp like any other
+    // LDS.128 (tools/probe_mma.cu), 16 warps x 16 of them were a third of the tile time.  (CW == 32 has no registers for that.)
+    constexpr bool REGC = (CW == 16);
+    uint32_t bx[REGC ? CW : 1];
+    double mm[REGC ? CW : 1];
+    if constexpr (REGC) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        const hawq_chan ch = p.chan[n0 + cg * CW + j];
+        bx[j] = (uint32_t)ch.bias + 0x80000000u;
+        mm[j] = dyadic_to_double(ch.m, ch.e);
+      }
+    }
 
     const bool elect_x = (ew == 0 && lane == 0);     // issues the TMA stores of the epilogue
     if constexpr (EPI == C1_REQ) {
@@ -292,9 +306,14 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
         int q[CW];
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
-          const double2 cm = cst[j];
-          const double d = __hiloint2double(0x43300000, acc[j] ^ 0x80000000) - cm.x;
-          q[j] = __double2loint(__fma_rn(d, cm.y, kMagic));
+          if constexpr (REGC) {     // 2^52 + (acc + bias + 2^31) - (2^52 + 2^31): exact, |acc + bias| < 2^31 by the bias bound
+            const double d = __hiloint2double(0x43300000, acc[j] + bx[j]) - kOffS;
+            q[j] = __double2loint(__fma_rn(d, mm[j], kMagic));
+          } else {
+            const double2 cm = cst[j];
+            const double d = __hiloint2double(0x43300000, acc[j] ^ 0x80000000) - cm.x;
+            q[j] = __double2loint(__fma_rn(d, cm.y, kMagic));
+          }
         }
         uint32_t w[CW / 4];
         if (clamp_mode == 1) {              // [0, hi]: unsigned byte saturation, then a per-byte min
@@ -349,9 +368,13 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
       const double low_M = dyadic_to_double(p.low_m, p.low_e), res_M = dyadic_to_double(p.res_m, p.res_e);
       const double low_C = kMagic - kOffU * low_M, res_C = kMagic - kOffU * res_M;
       const bool sat8 = p.sat_pack != 0 && p.low_bits == 8 && p.low_hi == 127 && p.low_lo <= 0;
+      // ... and with clamp [<= 0, hi <= 255] (4-bit values in byte containers) the u8 saturation followed by a per-byte min
+      const bool satu = p.sat_pack != 0 && p.low_bits == 8 && !sat8 && p.low_lo <= 0 && p.low_hi >= 0 && p.low_hi <= 255;
+      const uint32_t hi4 = (uint32_t)(p.low_hi & 255) * 0x01010101u;
       const int l_lo = p.low_lo, l_hi = p.low_hi;
       auto ratio_ok = [](uint32_t m_, int e_) { return m_ == 0u || e_ >= (WIDE ? 11 : 31); };
       bad |= !p.relu | !ratio_ok(p.res_m, p.res_e) | (p.res_m != 0u && p.res_e > 51);
+      if constexpr (WIDE) bad |= !(res_M < 16384.0);
       if (p.low_bits) bad |= !dyadic_is_fast(p.low_m, p.low_e) | (p.low_m != 0u && p.low_e > 51);
       // residual tile in shared memory: [chunk of 64 columns][128 rows][128 B], SWIZZLE_128B; this thread's CW columns
       const uint32_t r_chunk = (uint32_t)(cg * CW) / 64, r_piece0 = ((uint32_t)(cg * CW) % 64) / 8;
@@ -384,19 +407,25 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
           int y[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const double2 cm = cst[i * 8 + k];
-            const double d = __hiloint2double(0x43300000, acc[i * 8 + k] ^ 0x80000000) - cm.x;
-            const double qv = __fma_rn(d, cm.y, kMagic);
-            const int v = __double2loint(qv);
+            double qv;
+            if constexpr (REGC) {
+              qv = __fma_rn(__hiloint2double(0x43300000, acc[i * 8 + k] + bx[i * 8 + k]) - kOffS, mm[i * 8 + k], kMagic);
+            } else {
+              const double2 cm = cst[i * 8 + k];
+              qv = __fma_rn(__hiloint2double(0x43300000, acc[i * 8 + k] ^ 0x80000000) - cm.x, cm.y, kMagic);
+            }
+            int v = __double2loint(qv);
             const int r16 = (k & 1) ? (int)(rr[k >> 1] >> 16) : (int)(rr[k >> 1] & 0xFFFF);
             const double qr = __fma_rn(__hiloint2double(0x43300000, r16), res_M, res_C);
             const int vr = __double2loint(qr);
-            const int sum = v + vr;
             if constexpr (WIDE) {
+              // the main term may leave int32 (ratio > 1): exact per-value check.  The identity term cannot (0 <= r < 2^16 and
+              // res ratio < 2^14, checked once above: vr < 2^30), and with v capped at 2^30 the sum cannot wrap: a capped value
+              // is far above 65535 and raises HAWQ_FLAG_RESIDUAL_OVERFLOW through ymax like any other overflow of the stream
               ovf |= (__double2hiint(qv) + (int)((uint32_t)v >> 31)) ^ 0x43380000;
-              ovf |= (__double2hiint(qr) + (int)((uint32_t)vr >> 31)) ^ 0x43380000;
-              ovf |= ((v ^ sum) & (vr ^ sum)) >> 31;                   // the sum itself wrapped
+              v = min(v, 1 << 30);
             }
+            const int sum = v + vr;
             y[k] = max(sum, 0);
             ymax = max(ymax, y[k]);
           }
@@ -414,6 +443,14 @@ __global__ void __launch_bounds__(c1_threads(A4, EPI), 1) conv1x1_kernel(const C
               asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(lw[2 * i]) : "r"(q[1]), "r"(q[0]), "r"(h0));
               asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(h1) : "r"(q[7]), "r"(q[6]), "r"(0));
               asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(lw[2 * i + 1]) : "r"(q[5]), "r"(q[4]), "r"(h1));
+            } else if (satu) {
+              uint32_t h0, h1, o0, o1;
+              asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(h0) : "r"(q[3]), "r"(q[2]), "r"(0));
+              asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(o0) : "r"(q[1]), "r"(q[0]), "r"(h0));
+              asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(h1) : "r"(q[7]), "r"(q[6]), "r"(0));
+              asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(o1) : "r"(q[5]), "r"(q[4]), "r"(h1));
+              lw[2 * i] = __vminu4(o0, hi4);
+              lw[2 * i + 1] = __vminu4(o1, hi4);
             } else {
 #pragma unroll
               for (int k = 0; k < 8; ++k) q[k] = clampi(q[k], l_lo, l_hi);

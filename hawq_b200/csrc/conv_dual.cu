@@ -49,12 +49,14 @@ static bool plan_for(int bn, bool a4, int KT1, int KT2, int low_bits, DualPlan* 
   for (int kc = 4; kc >= 1; --kc) {
     if (g % kc) continue;
     const int a_stage = kc * 128 * 64;
-    for (int ns = (kc == 4 ? 3 : DUAL_MAX_STAGES); ns >= 2; --ns) {
+    for (int ns = (kc == 4 ? 3 : DUAL_MAX_STAGES); ns >= 2; --ns)
+    for (int obufs = 2; obufs >= 1; --obufs) {       // double-buffered output staging where it costs no activation stage
       int off = round_up(w_bytes, 1024);
       p.off_a = off; off += ns * a_stage + 8192;        // + slack: the MMA reads 128 rows from k-tile blocks of TR rows
       p.off_packed = off; off += a4 ? ns * (a_stage / 2) : 0;
-      p.off_y = off; off += y_bytes;
-      p.off_low = off; off += low_bytes;
+      p.off_y = off; off += obufs * y_bytes;
+      p.off_low = off; off += obufs * low_bytes;
+      p.out_bufs = obufs; p.y_stride = y_bytes; p.low_stride = low_bytes;
       p.off_cst = off; off += cst;
       p.off_bar = off; off += bars;
       const int total = off + 1024;

@@ -29,6 +29,7 @@ struct DualParams {
   int w1_boxes, w1_box_kt, w2_boxes, w2_box_kt;
   int low_bits; uint32_t low_m; int low_e, low_lo, low_hi;
   int sat_pack;
+  int out_bufs, y_stride, low_stride;   // staged output tiles (2 = double-buffered), bytes between the buffers
   int off_a, off_packed, off_y, off_low, off_cst, off_bar;   // shared-memory carve-up (weights at 0: [W1 | W2])
 };
 
@@ -260,6 +261,9 @@ __global__ void __launch_bounds__(dual_threads(A4), 1) conv_dual_kernel(const Du
     const double low_M = dyadic_to_double(p.low_m, p.low_e);
     const double low_C = kMagic - kOffU * low_M;
     const bool sat8 = p.sat_pack != 0 && p.low_bits == 8 && p.low_hi == 127 && p.low_lo <= 0;
+    // ... and with clamp [<= 0, hi <= 255] (4-bit values in byte containers) the u8 saturation followed by a per-byte min
+    const bool satu = p.sat_pack != 0 && p.low_bits == 8 && !sat8 && p.low_lo <= 0 && p.low_hi >= 0 && p.low_hi <= 255;
+    const uint32_t hi4 = (uint32_t)(p.low_hi & 255) * 0x01010101u;
     const int l_lo = p.low_lo, l_hi = p.low_hi;
     if (p.low_bits) bad |= !dyadic_is_fast(p.low_m, p.low_e) | (p.low_m != 0u && p.low_e > 51);
     const uint32_t r_chunk = (uint32_t)(cg * CW) / 64, r_piece0 = ((uint32_t)(cg * CW) % 64) / 8;
@@ -316,6 +320,14 @@ __global__ void __launch_bounds__(dual_threads(A4), 1) conv_dual_kernel(const Du
               asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(lw[2 * g8]) : "r"(q[1]), "r"(q[0]), "r"(h0));
               asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(h1) : "r"(q[7]), "r"(q[6]), "r"(0));
               asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(lw[2 * g8 + 1]) : "r"(q[5]), "r"(q[4]), "r"(h1));
+            } else if (satu) {
+              uint32_t h0, h1, o0, o1;
+              asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(h0) : "r"(q[3]), "r"(q[2]), "r"(0));
+              asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(o0) : "r"(q[1]), "r"(q[0]), "r"(h0));
+              asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(h1) : "r"(q[7]), "r"(q[6]), "r"(0));
+              asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(o1) : "r"(q[5]), "r"(q[4]), "r"(h1));
+              lw[2 * g8] = __vminu4(o0, hi4);
+              lw[2 * g8 + 1] = __vminu4(o1, hi4);
             } else {
 #pragma unroll
               for (int k = 0; k < 8; ++k) q[k] = clampi(q[k], l_lo, l_hi);
@@ -326,16 +338,18 @@ __global__ void __launch_bounds__(dual_threads(A4), 1) conv_dual_kernel(const Du
         }
       }
       // stage y ([64-column chunk][TR rows][128 B], SWIZZLE_128B) and the low-bit tile; one TMA store each per tile
-      if (elect_x) bulk_wait_read_all();                        // the previous tile's stores have finished reading the staging tiles
+      const uint32_t y_off = p.off_y + (p.out_bufs == 2 ? (t & 1) * p.y_stride : 0);
+      const uint32_t low_off = p.off_low + (p.out_bufs == 2 ? (t & 1) * p.low_stride : 0);
+      if (elect_x) { if (p.out_bufs == 2) bulk_wait_read_1(); else bulk_wait_read_all(); }   // the stores that last read these staging tiles are done
       asm volatile("bar.sync 1, %0;" ::"n"(DUAL_EPI_WARPS * 32));
       if (valid_row) {
         // the staged tile is [64-column chunk][TR rows][128 B]; the swizzle is a function of the shared-memory address, and a
         // chunk of TR rows need not start on a 1024-byte boundary: index it as one tile of (chunk * TR + row) rows
         const int yrow = (int)r_chunk * p.TR + row;
 #pragma unroll
-        for (int i = 0; i < CW / 8; ++i) *reinterpret_cast<uint4*>(smem + p.off_y + tile_piece_off(128, yrow, (int)r_piece0 + i)) = yo[i];
+        for (int i = 0; i < CW / 8; ++i) *reinterpret_cast<uint4*>(smem + y_off + tile_piece_off(128, yrow, (int)r_piece0 + i)) = yo[i];
         if (p.low_bits) {
-          uint8_t* lt = smem + p.off_low;
+          uint8_t* lt = smem + low_off;
           const int rb_low = BN * p.low_bits / 8;                 // 128 / 64 / 32
           if (p.low_bits == 8) {
 #pragma unroll
@@ -355,8 +369,8 @@ __global__ void __launch_bounds__(dual_threads(A4), 1) conv_dual_kernel(const Du
       asm volatile("bar.sync 1, %0;" ::"n"(DUAL_EPI_WARPS * 32));
       if (elect_x) {
         const int m0 = (slot + t * p.ctas_per_n) * p.TR;
-        tma_store_3d(&maps.y, 0, m0, n0 / 64, smem_base + p.off_y);
-        if (p.low_bits) tma_store_2d(&maps.low, n0 * p.low_bits / 8, m0, smem_base + p.off_low);
+        tma_store_3d(&maps.y, 0, m0, n0 / 64, smem_base + y_off);
+        if (p.low_bits) tma_store_2d(&maps.low, n0 * p.low_bits / 8, m0, smem_base + low_off);
         bulk_commit();
       }
     }

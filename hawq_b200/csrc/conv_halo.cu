@@ -9,11 +9,11 @@
 namespace hawq {
 
 static thread_local char g_halo_err[256] = "";
-static long long* g_halo_trace = nullptr;      // device buffer [3][64][4], allocated on first use when HAWQ_B200_HALO_TRACE=1
+static long long* g_halo_trace = nullptr;      // device buffer [4][64][4], allocated on first use when HAWQ_B200_HALO_TRACE=1
 
 int halo_read_trace(long long* host_out, int n) {
   if (!g_halo_trace) return 0;
-  if (n > 3 * 64 * 4) n = 3 * 64 * 4;
+  if (n > 4 * 64 * 4) n = 4 * 64 * 4;
   cudaDeviceSynchronize();
   cudaMemcpy(host_out, g_halo_trace, sizeof(long long) * n, cudaMemcpyDeviceToHost);
   return n;
@@ -118,7 +118,8 @@ int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_
   const int K = 9 * d->Cin;
   HaloPlan plan;
   memset(&plan, 0, sizeof(plan));
-  if (!((d->Cout % 128 == 0 && plan_for(128, a4, K, wp, R, &plan)) || plan_for(64, a4, K, wp, R, &plan))) return 1;
+  static const bool narrow = [] { const char* v = getenv("HAWQ_B200_BN"); return v && atoi(v) == 64; }();   // experiment switch: 64-channel blocks
+  if (!((d->Cout % 128 == 0 && !narrow && plan_for(128, a4, K, wp, R, &plan)) || plan_for(64, a4, K, wp, R, &plan))) return 1;
   HaloParams& p = plan.p;
   p.chan = chan; p.out = (uint8_t*)out; p.status = status;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cout = d->Cout; p.chunks = d->Cin / 64; p.R = R; p.wp = wp;
@@ -134,8 +135,8 @@ int launch_conv_halo(int sm_count, const hawq_conv_desc* d, const hawq_epilogue_
   p.relu = ep->relu; p.out_bits = ep->out_bits; p.lo = ep->clamp_lo; p.hi = ep->clamp_hi;
 
   static const bool tracing = [] { const char* e = getenv("HAWQ_B200_HALO_TRACE"); return e && e[0] == '1'; }();
-  if (tracing && !g_halo_trace) { cudaMalloc(&g_halo_trace, sizeof(long long) * 3 * 64 * 4); }
-  if (tracing) cudaMemsetAsync(g_halo_trace, 0, sizeof(long long) * 3 * 64 * 4, (cudaStream_t)stream);
+  if (tracing && !g_halo_trace) { cudaMalloc(&g_halo_trace, sizeof(long long) * 4 * 64 * 4); }
+  if (tracing) cudaMemsetAsync(g_halo_trace, 0, sizeof(long long) * 4 * 64 * 4, (cudaStream_t)stream);
   p.trace = tracing ? g_halo_trace : nullptr;
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) { snprintf(g_halo_err, sizeof(g_halo_err), "conv_halo: cuTensorMapEncodeTiled unavailable"); return HAWQ_ERR_CUDA; }

@@ -44,7 +44,7 @@ struct HaloParams {
   int packed_alloc;          // A4: bytes per packed patch buffer (multiple of 1024)
   int npb, nkb;              // int8 patch buffers, packed patch buffers (A4)
   int relu, out_bits, lo, hi;
-  long long* trace;          // debug timeline (hawq_debug_halo_trace): [3 roles][64][4] clock64 stamps of CTA 0, or null
+  long long* trace;          // debug timeline (hawq_debug_halo_trace): [4 roles][64][4] clock64 stamps of CTA 0, or null
   int w_rank3;               // weights tensor map: 1 = {Cin, Cout, 9 taps} 3-D view, 0 = plain [Cout][K] matrix
   int off_patch, off_packed, off_out, off_cst, off_bar;   // shared-memory carve-up (bytes from the 1024-aligned base; weights at 0)
 };
@@ -268,6 +268,20 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
     // this thread's output position is the same in every tile: position pos = TMEM lane, (y, x) inside the row group
     const int pos = quarter * 32 + lane;
     const double2* cst = sCst + cg * CW;
+    // CW == 16: the thread's 16 channel constants live in registers (bias folded into an integer add, ratio as a double) instead
+    // of one broadcast LDS.128 per value: a broadcast LDS.128 occupies the shared-memory pipe for 4 cycles per warp like any other
+    // LDS.128 (tools/probe_mma.cu), 16 warps x 16 of them were a third of the tile time.  (CW == 32 has no registers for that.)
+    constexpr bool REGC = (CW == 16);
+    uint32_t bx[REGC ? CW : 1];
+    double mm[REGC ? CW : 1];
+    if constexpr (REGC) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        const hawq_chan ch = p.chan[n0 + cg * CW + j];
+        bx[j] = (uint32_t)ch.bias + 0x80000000u;
+        mm[j] = dyadic_to_double(ch.m, ch.e);
+      }
+    }
     const bool elect_x = (ew == 0 && lane == 0);     // issues the TMA stores
     int n_img = slot / p.tiles_per_img, ti = slot - n_img * p.tiles_per_img;
     for (int t = 0; t < my_tiles; ++t) {
@@ -289,10 +303,16 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
       int q[CW];
 #pragma unroll
       for (int j = 0; j < CW; ++j) {
-        const double2 cm = cst[j];
-        const double d = __hiloint2double(0x43300000, acc[j] ^ 0x80000000) - cm.x;
-        q[j] = __double2loint(__fma_rn(d, cm.y, kMagic));
+        if constexpr (REGC) {       // 2^52 + (acc + bias + 2^31) - (2^52 + 2^31): exact, |acc + bias| < 2^31 by the bias bound
+          const double d = __hiloint2double(0x43300000, acc[j] + bx[j]) - kOffS;
+          q[j] = __double2loint(__fma_rn(d, mm[j], kMagic));
+        } else {
+          const double2 cm = cst[j];
+          const double d = __hiloint2double(0x43300000, acc[j] ^ 0x80000000) - cm.x;
+          q[j] = __double2loint(__fma_rn(d, cm.y, kMagic));
+        }
       }
+      if (ew == 0 && lane == 0) stamp(3, t, 0);
       uint32_t w[CW / 4];
       if (clamp_mode == 1) {              // [0, hi]: unsigned byte saturation, then a per-byte min
 #pragma unroll
@@ -320,7 +340,9 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
       // out of bounds of the output tensor and are clipped by the TMA unit
       const int rb_out = BN * p.out_bits / 8;                  // 128 / 64 / 32
       if (elect_x) bulk_wait_read_all();                        // the previous tile's store has finished reading the staging tile
+      if (ew == 0 && lane == 0) stamp(3, t, 1);
       asm volatile("bar.sync 1, %0;" ::"n"(HALO_EPI_WARPS * 32));
+      if (ew == 0 && lane == 0) stamp(3, t, 2);
       uint8_t* lt = smem + p.off_out;
       if (p.out_bits == 8) {
 #pragma unroll
@@ -335,6 +357,7 @@ __global__ void __launch_bounds__(halo_threads(A4), 1) conv_halo_kernel(const Ha
         }
       }
       fence_proxy_async();
+      if (ew == 0 && lane == 0) stamp(3, t, 3);
       asm volatile("bar.sync 1, %0;" ::"n"(HALO_EPI_WARPS * 32));
       if (elect_x) {
         tma_store_4d(&omap, n0 * p.out_bits / 8, 0, ti * p.R, n_img, smem_base + p.off_out);

@@ -46,7 +46,8 @@ int launch_stem_tc(int sm_count, int N, int H, int W, const int8_t* x, const int
                    void* stream) {
   static const bool enabled = [] { const char* e = getenv("HAWQ_B200_STEMTC"); return !(e && e[0] == '0'); }();   // debugging switch
   if (!enabled) return 1;
-  if (W % 4 != 0 || W > 256 || W < 8 || H < 8) return 1;
+  // rows are fetched as whole uint32 words by TMA: the row pitch 3 * W and the base address must be multiples of 16 bytes
+  if (W % 16 != 0 || W > 256 || H < 8 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
   if ((y_bits != 16 && y_bits != 32) || (low_bits != 0 && low_bits != 4 && low_bits != 8)) return 1;
   if (low_bits && low_m != 0u && (low_e < 31 || low_e > 51)) return 1;
   StemParams p;
@@ -62,16 +63,21 @@ int launch_stem_tc(int sm_count, int N, int H, int W, const int8_t* x, const int
   p.raw_rows = 4 * p.PB + 7; p.raw_pitch = W * 3; p.pix_pitch = W + 8;
   p.lo = clamp_lo; p.hi = clamp_hi; p.y_bits = y_bits;
   p.low_bits = low_bits; p.low_m = low_m; p.low_e = low_e; p.low_lo = low_lo; p.low_hi = low_hi;
-  int off = 64 * 256;
-  p.off_raw = off; off += round_up(p.raw_rows * p.raw_pitch, 1024);
-  p.off_pix = off; off += round_up(p.raw_rows * p.pix_pitch * 4, 1024);
-  p.off_a = off; off += 2 * STEM_A_TILE;
-  p.off_rows = off; off += 4 * STEM_ROW_BYTES;
-  p.off_y = off; off += round_up(p.Wp * 64 * y_bits / 8, 1024);
-  p.off_low = off; off += round_up(p.Wp * 64, 1024);
-  p.off_cst = off; off += 64 * 16;
-  p.off_bar = off; off += 256;
-  const int total = off + 1024;
+  int total = 0;
+  for (int obufs = 2; obufs >= 1; --obufs) {       // first choice: double-buffered output staging
+    int off = 64 * 256;
+    p.off_raw = off; off += round_up(p.raw_rows * p.raw_pitch, 1024);
+    p.off_pix = off; off += round_up(p.raw_rows * p.pix_pitch * 4, 1024);
+    p.off_a = off; off += 2 * STEM_A_TILE;
+    p.off_rows = off; off += 3 * STEM_ROW_BYTES + round_up(p.Wc * 128, 1024);     // 4 row slots, the last one without the idle pixels
+    p.y_stride = round_up(p.Wp * 64 * y_bits / 8, 1024); p.low_stride = round_up(p.Wp * 64, 1024); p.out_bufs = obufs;
+    p.off_y = off; off += obufs * p.y_stride;
+    p.off_low = off; off += obufs * p.low_stride;
+    p.off_cst = off; off += 64 * 16;
+    p.off_bar = off; off += 256;
+    total = off + 1024;
+    if (total <= STEM_SMEM_MAX) break;
+  }
   if (total > STEM_SMEM_MAX) return 1;
 
   encode_tiled_fn enc = get_encode_tiled();

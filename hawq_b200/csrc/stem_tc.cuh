@@ -35,6 +35,7 @@ struct StemParams {
   int lo, hi;                // 16-bit clamp of quant_act_int32
   int y_bits;                // 16 | 32
   int low_bits; uint32_t low_m; int low_e, low_lo, low_hi;
+  int out_bufs, y_stride, low_stride;   // staged output tiles (2 = double-buffered, alternating per emitted pooled row), bytes between the buffers
   int off_raw, off_pix, off_a, off_rows, off_y, off_low, off_cst, off_bar;   // shared-memory carve-up (weights at 0)
 };
 
@@ -50,7 +51,7 @@ constexpr int STEM_MMA_WARP = STEM_BUILD_WARPS;
 constexpr int STEM_EPI_WARP0 = STEM_BUILD_WARPS + 1;
 constexpr int STEM_TC_THREADS = (STEM_BUILD_WARPS + 1 + STEM_EPI_WARPS) * 32;   // 800
 constexpr int STEM_A_TILE = 4 * 128 * 64;      // one convolution row: 4 k-tiles
-constexpr int STEM_ROW_BYTES = 128 * 128;      // one requantised convolution row: <= 128 pixels x 64 channels x int16
+constexpr int STEM_ROW_BYTES = 128 * 128;      // one requantised convolution row: <= 128 pixels x 64 channels x int16 (the last slot may be shorter: Wc pixels)
 
 __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const StemParams p, const __grid_constant__ StemMaps maps) {
   extern __shared__ uint8_t smem_raw[];
@@ -220,12 +221,21 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const StemP
     const double low_C = kMagic - kOffU * low_M;
     if (p.low_bits) bad |= !dyadic_is_fast(p.low_m, p.low_e) | (p.low_m != 0u && p.low_e > 51);
     const int px = quarter * 32 + lane;          // convolution pixel of this thread
-    const double2* cst = sCst + cg * 16;
+    // the thread's 16 channel constants live in registers (bias folded into an integer add, ratio as a double): one broadcast
+    // LDS.128 per value would occupy the shared-memory pipe for 4 cycles per warp (tools/probe_mma.cu), 1024 cycles per row
+    uint32_t bx[16];
+    double mm[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const hawq_chan ch = p.chan[cg * 16 + j];
+      bx[j] = (uint32_t)ch.bias + 0x80000000u;
+      mm[j] = dyadic_to_double(ch.m, ch.e);
+    }
     const bool elect_x = etid == 0;
     const int q_lo = max(p.lo, 0), q_hi = p.hi;  // clamp, then ReLU
     // pooling role of this thread: pooled pixel pp (8 threads per pixel), channels 8 * pc .. 8 * pc + 7
     const int pp = etid >> 3, pc = etid & 7;
-    uint32_t g = 0;
+    uint32_t g = 0, emitted = 0;
     for (int u = 0; u < my_units; ++u) {
       int n_img, p0, c_first, c_last;
       unit_rows(u, n_img, p0, c_first, c_last);
@@ -245,22 +255,26 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const StemP
           int q[2];
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            const double2 cm = cst[j + k];
-            const double d = __hiloint2double(0x43300000, acc[j + k] ^ 0x80000000) - cm.x;
-            q[k] = clampi(__double2loint(__fma_rn(d, cm.y, kMagic)), q_lo, q_hi);
+            const double d = __hiloint2double(0x43300000, acc[j + k] + bx[j + k]) - kOffS;      // exact: |acc + bias| < 2^31
+            q[k] = clampi(__double2loint(__fma_rn(d, mm[j + k], kMagic)), q_lo, q_hi);
           }
           w16[j >> 1] = (uint32_t)q[0] | ((uint32_t)q[1] << 16);     // 0 <= q <= 32767
         }
         // requantised row -> row ring slot c & 3: [pixel][64 channels] int16, 16-byte pieces XOR-swizzled by the pixel index
         uint8_t* rowp = smem + p.off_rows + (c & 3) * STEM_ROW_BYTES + px * 128;
-        *reinterpret_cast<uint4*>(rowp + (((2 * cg) ^ (px & 7)) << 4)) = make_uint4(w16[0], w16[1], w16[2], w16[3]);
-        *reinterpret_cast<uint4*>(rowp + (((2 * cg + 1) ^ (px & 7)) << 4)) = make_uint4(w16[4], w16[5], w16[6], w16[7]);
+        if (px < p.Wc) {                            // (the last ring slot only holds Wc pixels)
+          *reinterpret_cast<uint4*>(rowp + (((2 * cg) ^ (px & 7)) << 4)) = make_uint4(w16[0], w16[1], w16[2], w16[3]);
+          *reinterpret_cast<uint4*>(rowp + (((2 * cg + 1) ^ (px & 7)) << 4)) = make_uint4(w16[4], w16[5], w16[6], w16[7]);
+        }
         // a pooled row is complete after convolution row 2 * pr + 1 (or the last row of the image)
         const bool emit = (c & 1) || c == p.Hc - 1;
         if (!emit) continue;
         const int pr = c >> 1;
         if (pr < p0 || pr >= p0 + p.PB || pr >= p.Hp) continue;          // (row 2 * p0 - 1 only feeds the first pooled row of the band)
-        if (elect_x) bulk_wait_read_all();          // the previous pooled row's stores have finished reading the staging tiles
+        const uint32_t ob = p.out_bufs == 2 ? (emitted++ & 1) : 0;         // staging buffers alternate per emitted pooled row
+        const uint32_t y_off = p.off_y + ob * p.y_stride;
+        const uint32_t low_off = p.off_low + ob * p.low_stride;
+        if (elect_x) { if (p.out_bufs == 2) bulk_wait_read_1(); else bulk_wait_read_all(); }   // the stores that last read these staging tiles are done
         asm volatile("bar.sync 1, %0;" ::"n"(STEM_EPI_WARPS * 32));      // the three rows are complete, the staging tiles are free
         if (pp < p.Wp) {
           // rows 2 pr - 1, 2 pr, 2 pr + 1 and pixels 2 pp - 1, 2 pp, 2 pp + 1, clipped by duplication (all values are >= 0)
@@ -281,12 +295,12 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const StemP
           const int y[8] = {(int)(m.x & 0xFFFF), (int)(m.x >> 16), (int)(m.y & 0xFFFF), (int)(m.y >> 16),
                             (int)(m.z & 0xFFFF), (int)(m.z >> 16), (int)(m.w & 0xFFFF), (int)(m.w >> 16)};
           if (p.y_bits == 16) {                     // [Wp pixels][128 B], SWIZZLE_128B
-            *reinterpret_cast<uint4*>(smem + p.off_y + tile_piece_off(128, pp, pc)) = m;
+            *reinterpret_cast<uint4*>(smem + y_off + tile_piece_off(128, pp, pc)) = m;
           } else {                                  // int32: [2 chunks of 32 channels][Wp pixels][128 B]
             const int chunk = pc >> 2, piece = (pc & 3) * 2;
             const int yrow = chunk * p.Wp + pp;
-            *reinterpret_cast<uint4*>(smem + p.off_y + tile_piece_off(128, yrow, piece)) = make_uint4(y[0], y[1], y[2], y[3]);
-            *reinterpret_cast<uint4*>(smem + p.off_y + tile_piece_off(128, yrow, piece + 1)) = make_uint4(y[4], y[5], y[6], y[7]);
+            *reinterpret_cast<uint4*>(smem + y_off + tile_piece_off(128, yrow, piece)) = make_uint4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<uint4*>(smem + y_off + tile_piece_off(128, yrow, piece + 1)) = make_uint4(y[4], y[5], y[6], y[7]);
           }
           if (p.low_bits) {
             int q[8];
@@ -295,17 +309,17 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const StemP
               q[k] = clampi(__double2loint(__fma_rn(__hiloint2double(0x43300000, y[k]), low_M, low_C)), p.low_lo, p.low_hi);
             const uint32_t w0 = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
             const uint32_t w1 = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
-            if (p.low_bits == 8) *reinterpret_cast<uint2*>(smem + p.off_low + tile_piece_off(64, pp, pc >> 1) + (pc & 1) * 8) = make_uint2(w0, w1);
-            else *reinterpret_cast<uint32_t*>(smem + p.off_low + tile_piece_off(32, pp, pc >> 2) + (pc & 3) * 4) = pack_nibbles8(w0, w1);
+            if (p.low_bits == 8) *reinterpret_cast<uint2*>(smem + low_off + tile_piece_off(64, pp, pc >> 1) + (pc & 1) * 8) = make_uint2(w0, w1);
+            else *reinterpret_cast<uint32_t*>(smem + low_off + tile_piece_off(32, pp, pc >> 2) + (pc & 3) * 4) = pack_nibbles8(w0, w1);
           }
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, %0;" ::"n"(STEM_EPI_WARPS * 32));
         if (elect_x) {
           const int row0 = (n_img * p.Hp + pr) * p.Wp;
-          if (p.y_bits == 16) tma_store_2d(&maps.y, 0, row0, smem_base + p.off_y);
-          else tma_store_3d(&maps.y, 0, row0, 0, smem_base + p.off_y);
-          if (p.low_bits) tma_store_2d(&maps.low, 0, row0, smem_base + p.off_low);
+          if (p.y_bits == 16) tma_store_2d(&maps.y, 0, row0, smem_base + y_off);
+          else tma_store_3d(&maps.y, 0, row0, 0, smem_base + y_off);
+          if (p.low_bits) tma_store_2d(&maps.low, 0, row0, smem_base + low_off);
           bulk_commit();
         }
       }

@@ -580,7 +580,7 @@ def test_conv_dual_stationary_weights(geom, a_bits, flag):
     ops.reset_status(0)
 
 
-@pytest.mark.parametrize("shape", [(2, 224, 224), (3, 64, 48), (1, 32, 192), (5, 20, 12), (2, 58, 36)])
+@pytest.mark.parametrize("shape", [(2, 224, 224), (3, 64, 48), (1, 32, 192), (5, 20, 16), (2, 58, 32)])
 def test_stem_pool_fused(shape):
     """hawq_stem_pool_i8 (tcgen05 stem: conv + max-pool + 16-bit requant + ReLU + low-bit copy) == hawq_stem_conv_i8 followed by
     hawq_maxpool_requant of the ABI model, for the uint16 and the int32 stream, 8 / 4-bit and no low copy, bands that end inside the image."""
@@ -601,3 +601,23 @@ def test_stem_pool_fused(shape):
         for a, b, k_ in zip(cs, gs, keys):
             assert torch.equal(a, b), (shape, y_bits, low_bits, k_, int((a != b).sum()))
     assert ops.get_status(0) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(5, 20, 12), (2, 58, 36), (1, 16, 272)])
+def test_stem_pool_declines_shapes_outside_the_kernel(shape):
+    """Row pitches that are not a multiple of 16 bytes (TMA) and rows wider than the shared-memory budget: hawq_stem_pool_i8 answers
+    HAWQ_ERR_UNSUPPORTED without launching anything (the host then runs hawq_stem_conv_i8 + hawq_maxpool_requant)."""
+    from hawq_b200._lib import HawqError, ERR_UNSUPPORTED
+    n, h, w = shape
+    r = rng(7)
+    x = torch.from_numpy(r.randint(-128, 128, size=n * h * w * 3).astype(np.int8)).cuda()
+    wt = torch.zeros((64, 8, 8, 4), dtype=torch.int8).cuda()
+    chan = make_chan(r, 64, ratio_lo=0.05, ratio_hi=0.8).cuda()
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    po, qo = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
+    y = torch.zeros(n * po * qo * 64, dtype=torch.int16, device="cuda")
+    with pytest.raises(HawqError) as err:
+        ops.stem_pool(x, wt, chan, (-32768, 32767), n, h, w, 16, y, 0, (0, 1), (0, 0), None)
+    assert err.value.code == ERR_UNSUPPORTED
+    assert int(y.abs().max()) == 0

@@ -34,7 +34,7 @@ for what in "$@"; do
     bench*)
       IFS=: read -r _ arch scheme batch a4 <<< "$what"
       arch=${arch:-resnet50}; scheme=${scheme:-uniform8}; batch=${batch:-128}; a4=${a4:-byte}
-      tag=${arch}_${scheme}_b${batch}; [[ $a4 == packed ]] && tag=${tag}_packed
+      tag=${arch}_${scheme}_b${batch}${TAG:-}; [[ $a4 == packed ]] && tag=${tag}_packed
       timeout 600 python bench.py --arch $arch --scheme $scheme --batch $batch --a4-storage $a4 --steps ${STEPS:-50} --warmup 5 --no-cpu-baseline --detail gpurun_out/detail_$tag.json > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
       echo "bench $tag exit $?"; python - <<PY
 import json

@@ -26,11 +26,12 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); ops.conv2d(x, d, ep, wd, chan, out=out); e1.record(); torch.cuda.synchronize()
 print("launch %.1f us" % (e0.elapsed_time(e1) * 1e3))
-buf = (C.c_int64 * (3 * 64 * 4))()
-got = _lib.load().hawq_debug_halo_trace(C.cast(buf, C.c_void_p), 3 * 64 * 4)
-t = np.array(buf[:got], dtype=np.int64).reshape(3, 64, 4)
+buf = (C.c_int64 * (4 * 64 * 4))()
+got = _lib.load().hawq_debug_halo_trace(C.cast(buf, C.c_void_p), 4 * 64 * 4)
+t = np.array(buf[:got], dtype=np.int64).reshape(4, 64, 4)
 t0 = t[t > 0].min()
-for role, name, evs in ((0, "producer", "wait_empty got_empty issued -"), (1, "mma", "wait_tempty wait_pfull got_pfull issued"), (2, "epilogue", "wait_tfull got_tfull released stored")):
+for role, name, evs in ((0, "producer", "wait_empty got_empty issued -"), (1, "mma", "wait_tempty wait_pfull got_pfull issued"), (2, "epilogue", "wait_tfull got_tfull released stored"),
+                        (3, "epilogue detail", "math_done before_bar1 after_bar1 staged(before_bar2)")):
     print(name, "(cycles since first stamp; columns: %s)" % evs)
-    for i in range(12):
+    for i in range(int(os.environ.get("TRACE_ROWS", "12"))):
         print("  %2d " % i + " ".join("%8d" % (v - t0 if v > 0 else -1) for v in t[role, i]))
