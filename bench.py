@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-batch8", action="store_true", help="skip the latency-regime leg (batch 8 per GPU) of the JSON line")
     ap.add_argument("--residual-bits", type=int, default=16)
     ap.add_argument("--a4-storage", default="byte", choices=["byte", "packed"],
                     help="HBM container of 4-bit activations: one value per byte (default, consumed directly by the int8 tensor-core kernels) or packed nibbles expanded on chip")
@@ -201,6 +202,19 @@ def workload_config(a, world, detail):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+def start_watchdog(seconds, what):
+    """A multi-rank run that stops making progress (a collective some rank never enters) must end by itself: after `seconds`
+    the process prints why and exits with status 3 instead of waiting for an outer timeout."""
+    def fire():
+        sys.stderr.write("bench.py watchdog: %s still running after %d s - aborting\n" % (what, seconds))
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def run_ours(a):
     import torch.distributed as dist
     import hawq_b200 as hb
@@ -219,6 +233,7 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        start_watchdog(int(os.environ.get("HAWQ_BENCH_WATCHDOG_S", "420")), "rank %d of %d" % (rank, world))
     build_library()
 
     B = a.batch
@@ -288,13 +303,23 @@ def run_ours(a):
 
     # ---- parity of the timed configuration: the logits of one timed batch (CUDA graph, uint16 stream, fused kernels) against an
     # eager run of the same batch on the int32 residual stream without ratio promises (generic saturating kernels)
-    parity = None
-    if rank == 0:
-        parity = parity_check(hb, q, eng, dev_pool[0])
+    # (N > 1: the replay contains the all-gather, so every rank takes part; each checks its own shard, rank 0 reports)
+    parity = parity_check(hb, q, eng, dev_pool[0], rank)
+    if world > 1:
+        ok = torch.tensor([1 if parity["bit_equal"] else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        parity["bit_equal"] = bool(int(ok.item()))
+        parity["ranks_checked"] = world
+    if rank != 0:
+        parity = None
     # ---- roofline leg: per-launch CUDA-event timing of an eager (un-graphed) pass, same stream, same buffers
     roof, detail = None, None
     if rank == 0 and not a.no_roofline:
         roof, detail = roofline_leg(hb, ops, q, dev_pool, a, ms / a.steps)
+    # ---- latency regime (the reference's own CPU benchmark runs batch 8): same model, 8 images per GPU per step
+    small = None
+    if rank == 0 and not a.no_batch8 and B != 8:
+        small = small_batch_leg(hb, q, dev, s_in, a, 8)
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
         ips, threads, sec, cpu_b, _ = cpu_forward_rate(a.arch, a.scheme, a.cpu_batch, 3, 1, budget_s=20.0)
@@ -323,22 +348,66 @@ def run_ours(a):
                 "clocks": clk,
                 "tensor": {"achieved_tops": 2 * macs * value / 1e12, "nominal_int8_peak_tops": INT8_TC_PEAK_OPS / 1e12,
                            "frac_of_nominal": 2 * macs * value / INT8_TC_PEAK_OPS},
-                "parity": parity, "roofline": roof, "cpu_baseline": cpu}
+                "parity": parity, "roofline": roof, "cpu_baseline": cpu, "batch8": small}
         print(json.dumps(line))
         if a.detail and detail is not None:
             with open(a.detail, "w") as f:
                 json.dump(detail, f, indent=1)
     if world > 1:
-        dist.destroy_process_group()
+        # Every rank is done once this barrier returns.  The process ends here: tearing the NCCL communicator down while CUDA
+        # graphs that captured its kernels are still alive blocked on the GPU box (seen at N = 2), and nothing is left to clean up.
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
-def parity_check(hb, q, eng, x):
+def small_batch_leg(hb, q, dev, s_in, a, b):
+    """The same network at `b` images per step on this GPU (own CUDA graph): device-resident and end-to-end images/s, timed like
+    the headline numbers (CUDA events on the launch stream, synchronised on both sides)."""
+    g = torch.Generator().manual_seed(99)
+    host = [torch.clamp(torch.round(torch.randn(b, 224, 224, 3, generator=g) / s_in), -128, 127).to(torch.int8).pin_memory() for _ in range(4)]
+    devs = [t.to(dev) for t in host]
+    eng = hb.compile_model(q, devs[0], residual_bits=a.residual_bits)
+    steps = max(4 * a.steps, 100)
+    for i in range(10):
+        eng.run_async(devs[i % 4])
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        eng.run_async(devs[i % 4])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    flag = int(eng.flag.item())
+    for _ in eng.run_pipelined(host[i % 4] for i in range(3)):
+        pass
+    torch.cuda.synchronize(dev)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    acc = 0.0
+    for res in eng.run_pipelined(host[i % 4] for i in range(steps)):
+        acc += float(res[0, 0])
+    f1.record()
+    torch.cuda.synchronize(dev)
+    ms2 = f0.elapsed_time(f1)
+    return {"batch": b, "n_gpus": 1, "steps": steps, "value": b * steps / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / steps,
+            "e2e": {"value": b * steps / (ms2 / 1e3), "unit": "images/s", "ms_per_step": ms2 / steps,
+                    "h2d_bytes_per_step": int(host[0].numel()), "d2h_bytes_per_step": int(b * 1000 * 4 + 4)},
+            "gpu_launches_per_step": eng.gpu_launches, "overflow_flag_seen": bool(flag & 1),
+            "note": "latency-bound regime: the per-step working set is L2-resident, %d kernels per step" % eng.gpu_launches}
+
+
+def parity_check(hb, q, eng, x, rank=0):
     """Logits of one timed batch through the benchmarked path vs an eager (un-graphed) run of the same batch with int32
     residuals and no ratio promises.  Two independent kernel sets (fused tcgen05 / generic IMMA) must agree bit for bit."""
     from hawq_b200 import qtensor
     from hawq_b200.qtensor import IntActivation, Node
     fast = eng(x).clone()
     n, h, w, c = x.shape
+    if fast.shape[0] != n:                 # gathered logits of the whole sharded batch: this rank's shard
+        fast = fast[rank * n:(rank + 1) * n]
     with torch.no_grad(), qtensor.engine_mode(residual_bits=32, fast_kernels=False, checked=False):
         ref = q(IntActivation(Node("int", (n, c, h, w), data=x.view(-1), bits=8, signed=True), x.device))
     torch.cuda.synchronize()

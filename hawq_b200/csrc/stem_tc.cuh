@@ -221,16 +221,7 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const StemP
     const double low_C = kMagic - kOffU * low_M;
     if (p.low_bits) bad |= !dyadic_is_fast(p.low_m, p.low_e) | (p.low_m != 0u && p.low_e > 51);
     const int px = quarter * 32 + lane;          // convolution pixel of this thread
-    // the thread's 16 channel constants live in registers (bias folded into an integer add, ratio as a double): one broadcast
-    // LDS.128 per value would occupy the shared-memory pipe for 4 cycles per warp (tools/probe_mma.cu), 1024 cycles per row
-    uint32_t bx[16];
-    double mm[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const hawq_chan ch = p.chan[cg * 16 + j];
-      bx[j] = (uint32_t)ch.bias + 0x80000000u;
-      mm[j] = dyadic_to_double(ch.m, ch.e);
-    }
+    const double2* cst = sCst + cg * 16;
     const bool elect_x = etid == 0;
     const int q_lo = max(p.lo, 0), q_hi = p.hi;  // clamp, then ReLU
     // pooling role of this thread: pooled pixel pp (8 threads per pixel), channels 8 * pc .. 8 * pc + 7
@@ -255,8 +246,9 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) stem_tc_kernel(const StemP
           int q[2];
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            const double d = __hiloint2double(0x43300000, acc[j + k] + bx[j + k]) - kOffS;      // exact: |acc + bias| < 2^31
-            q[k] = clampi(__double2loint(__fma_rn(d, mm[j + k], kMagic)), q_lo, q_hi);
+            const double2 cm = cst[j + k];
+            const double d = __hiloint2double(0x43300000, acc[j + k] ^ 0x80000000) - cm.x;
+            q[k] = clampi(__double2loint(__fma_rn(d, cm.y, kMagic)), q_lo, q_hi);
           }
           w16[j >> 1] = (uint32_t)q[0] | ((uint32_t)q[1] << 16);     // 0 <= q <= 32767
         }

@@ -47,7 +47,9 @@ PY
       tail -3 gpurun_out/bench_$tag.err;;
     ncu)
       timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-roofline > gpurun_out/ncu_bench.log 2>&1
-      echo "ncu list exit $?";;
+      echo "ncu list exit $?"
+      python tools/summarize_ncu.py gpurun_out/launches.csv "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-roofline" --json gpurun_out/ncu_traffic_entry.json > gpurun_out/ncu_launch_summary.txt 2>&1
+      tail -12 gpurun_out/ncu_launch_summary.txt;;
     ncufull:*)
       rx=${what#ncufull:}
       timeout 600 ncu --set full --import-source on --clock-control none -k regex:$rx -s ${NCU_SKIP:-8} -c ${NCU_COUNT:-4} -o gpurun_out/prof_$rx -f python tools/profile_forward.py --forwards 2 > gpurun_out/prof_$rx.log 2>&1

@@ -54,7 +54,8 @@ def main():
         print(line)
     fams = OrderedDict()
     for k, a in agg.items():
-        name = "conv_tc_kernel" if "conv_tc_kernel" in k else "conv_halo_kernel" if "conv_halo_kernel" in k else "conv1x1_kernel" if "conv1x1_kernel" in k else "conv_dual_kernel" if "conv_dual_kernel" in k else None
+        # family names as bench.py reports them (roofline.kernel / roofline.families)
+        name = next((fam for fam in ("conv_tc_kernel", "conv_halo_kernel", "conv1x1_kernel", "conv_dual_kernel", "stem_tc_kernel") if fam in k), None)
         if name is None:
             continue
         fam = fams.setdefault(name, {"launches": 0, "us": 0.0, "rd": 0.0, "wr": 0.0})
