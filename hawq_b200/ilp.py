@@ -122,7 +122,7 @@ def latency_table_from_detail(detail4, detail8, arch, parameters):
     last = "quant_convbn3" if bottleneck else "quant_convbn2"
     tables = []
     for det in (detail4, detail8):
-        launches = iter([l for l in det["layers"] if l["kernel"].startswith(("hawq_conv2d", "conv_"))])
+        launches = iter([l for l in det["layers"] if l["kernel"].startswith(("hawq_conv2d", "conv"))])
         lat = np.zeros(len(names))
         units = sorted({n.rsplit(".", 1)[0] for n in names}, key=lambda u: [int(t) for t in u.replace("stage", "").replace("unit", "").split(".")])
         for u in units:
