@@ -1,8 +1,8 @@
 """Bit-allocation tables and the attribute-stamping contract.
 
 The tables are the reference's ``bit_config_dict`` entries for the ResNet
-family (reference ``bit_config.py:3-3054``), carried as data in
-``data/bit_configs_resnet.json`` (module name -> 4 / 8 / 16, optional 'hook').
+family (reference ``bit_config.py:3-3054``) and for MobileNetV2 (``:3602-4202``), carried as data in
+``data/bit_configs_resnet.json`` / ``data/bit_configs_mobilenetv2.json`` (module name -> 4 / 8 / 16, optional 'hook').
 
 ``stamp_bit_config`` reproduces how the reference trainer writes those numbers
 onto the quant modules by plain ``setattr`` (reference ``quant_train.py:264-299``):
@@ -12,7 +12,7 @@ are switched to 'asymmetric' (unsigned 0..15, no zero point).
 import json
 import os
 
-_DATA = os.path.join(os.path.dirname(__file__), "data", "bit_configs_resnet.json")
+_DATA = [os.path.join(os.path.dirname(__file__), "data", n) for n in ("bit_configs_resnet.json", "bit_configs_mobilenetv2.json")]
 _cache = None
 
 
@@ -20,8 +20,10 @@ def bit_config_dict():
     """{"bit_config_<arch>_<scheme>": {module_name: bits | (bits, 'hook')}} (insertion ordered)."""
     global _cache
     if _cache is None:
-        with open(_DATA) as f:
-            raw = json.load(f)
+        raw = {}
+        for path in _DATA:
+            with open(path) as f:
+                raw.update(json.load(f))
         out = {}
         for key, entries in raw.items():
             d = {}

@@ -108,3 +108,60 @@ def synthetic_batch(batch, seed, hw=224):
     """Seeded N(0,1) image batch, NCHW fp32 on CPU (the calibration / parity input)."""
     g = torch.Generator().manual_seed(seed)
     return torch.randn(batch, 3, hw, hw, generator=g)
+
+
+# ----------------------------------------------------------------------------- MobileNetV2 (pytorchcv `mobilenetv2_w1` layout)
+MOBILENETV2_CHANNELS = [[16], [24, 24], [32, 32, 32], [64, 64, 64, 64, 96, 96, 96], [160, 160, 160, 320]]
+
+
+class _DwConvBn(nn.Module):
+    def __init__(self, c, stride):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride, 1, groups=c, bias=False)
+        self.bn = nn.BatchNorm2d(c)
+
+
+class _LinearBottleneck(nn.Module):
+    def __init__(self, cin, cout, stride, expansion):
+        super().__init__()
+        mid = cin * 6 if expansion else cin
+        self.conv1 = _ConvBn(cin, mid, 1, 1, 0)
+        self.conv2 = _DwConvBn(mid, stride)
+        self.conv3 = _ConvBn(mid, cout, 1, 1, 0)
+
+
+class SyntheticMobileNetV2(nn.Module):
+    """Float skeleton with the attributes the quantized graph reads (reference ``utils/models/q_mobilenetv2.py:45-55,142-180``):
+    ``features.init_block.{conv,bn}``, ``features.stageN.unitM.convK.{conv,bn}``, ``features.final_block.{conv,bn}``,
+    ``features.final_pool``, ``output`` (a bias-free 1x1 convolution, as in pytorchcv)."""
+
+    def __init__(self, num_classes=1000):
+        super().__init__()
+        self.features = nn.Module()
+        self.features.init_block = _ConvBn(3, 32, 3, 2, 1)
+        cin = 32
+        for si, stage_channels in enumerate(MOBILENETV2_CHANNELS):
+            stage = nn.Module()
+            for ui, cout in enumerate(stage_channels):
+                stride = 2 if (ui == 0 and si != 0) else 1
+                setattr(stage, "unit%d" % (ui + 1), _LinearBottleneck(cin, cout, stride, expansion=(si != 0 or ui != 0)))
+                cin = cout
+            setattr(self.features, "stage%d" % (si + 1), stage)
+        self.features.final_block = _ConvBn(cin, 1280, 1, 1, 0)
+        self.features.final_pool = nn.AvgPool2d(kernel_size=7, stride=1)
+        self.output = nn.Conv2d(1280, num_classes, 1, bias=False)
+
+
+def synthetic_float_mobilenetv2(seed=0):
+    """Seeded float skeleton of MobileNetV2-1.0: default conv init + randomised BN (same recipe as the ResNets)."""
+    prev = torch.random.get_rng_state()
+    try:
+        torch.manual_seed(seed)
+        net = SyntheticMobileNetV2()
+        g = torch.Generator().manual_seed(seed + 1000)
+        with torch.no_grad():
+            randomize_bn_(net, g)
+    finally:
+        torch.random.set_rng_state(prev)
+    net.eval()
+    return net

@@ -382,3 +382,127 @@ class FakeQuantResNet:
         return dict(arch=self.arch, convs=convs, acts=acts, fc=fc, resize=dict(self.resize),
                     units_per_stage=list(self.units_per_stage), bottleneck=self.bottleneck,
                     init_name=self.init_name)
+
+
+class FakeQuantMobileNetV2:
+    """Restatement of Q_MobileNetV2 + Q_LinearBottleneck (utils/models/q_mobilenetv2.py:12-212) on a float model with the
+    pytorchcv attribute layout.  Module names match the reference's ``named_modules()`` (bit_config.py:3602-4202).
+    What differs from the ResNets: ReLU6 in the float domain before the QuantAct that follows a convolution (a clamp at 6.0 of
+    acc * scale, i.e. a per-channel clamp of the accumulator), depthwise convolutions (groups = channels), no activation after
+    conv3 and none after the residual sum (the 16-bit stream is signed), the unit input itself as identity operand, and a 1x1
+    QuantConv2d as classifier whose fp32 output are the logits."""
+
+    def __init__(self, float_model, bit_config, momentum=0.99):
+        self.acts, self.convs = {}, {}
+        f = float_model.features
+        self.acts["quant_input"] = ActState()
+        self.convs["init_block"] = ConvBnState(f.init_block.conv, f.init_block.bn)
+        self.acts["quant_act_int32"] = ActState()
+        self.units = []
+        s = 1
+        while hasattr(f, "stage%d" % s):
+            stage, u = getattr(f, "stage%d" % s), 1
+            while hasattr(stage, "unit%d" % u):
+                unit = getattr(stage, "unit%d" % u)
+                p = "features.stage%d.unit%d" % (s, u)
+                c1, c3 = unit.conv1.conv, unit.conv3.conv
+                residual = (c1.in_channels == c3.out_channels) and unit.conv2.conv.stride[0] == 1
+                self.units.append((p, residual))
+                self.acts[p + ".quant_act"] = ActState()
+                self.convs[p + ".conv1"] = ConvBnState(unit.conv1.conv, unit.conv1.bn)
+                self.acts[p + ".quant_act1"] = ActState()
+                self.convs[p + ".conv2"] = ConvBnState(unit.conv2.conv, unit.conv2.bn)
+                self.acts[p + ".quant_act2"] = ActState()
+                self.convs[p + ".conv3"] = ConvBnState(unit.conv3.conv, unit.conv3.bn)
+                self.acts[p + ".quant_act_int32"] = ActState()
+                u += 1
+            s += 1
+        self.acts["quant_act_before_final_block"] = ActState()
+        self.convs["features.final_block"] = ConvBnState(f.final_block.conv, f.final_block.bn)
+        self.acts["quant_act_int32_final"] = ActState()
+        self.pool = f.final_pool
+        self.acts["quant_act_output"] = ActState()
+        self.out = ConvState(float_model.output)
+        seen = 0
+        for name, v in bit_config.items():       # stamp (quant_train.py:264-299)
+            bits = v[0] if isinstance(v, tuple) else v
+            if name in self.acts:
+                a = self.acts[name]
+                a.bits, a.momentum = bits, momentum
+                a.mode = 'asymmetric' if bits == 4 else 'symmetric'
+                seen += 1
+            elif name in self.convs:
+                self.convs[name].wbits = bits
+                seen += 1
+            elif name == "output":
+                self.out.wbits = bits
+                seen += 1
+            elif name.rsplit(".", 1)[0] in self.convs and name.rsplit(".", 1)[1] in ("conv", "bn"):
+                seen += 1      # the uniform tables also list `features.stage4.unit5.conv1.{conv,bn}` (bit_config.py:3690-3691): the
+                               # trainer stamps attributes onto the wrapped nn.Conv2d / BatchNorm2d, which nothing reads
+        assert seen == len(bit_config), (seen, len(bit_config))
+        self.trace = None
+
+    def freeze(self):
+        for a in self.acts.values():
+            a.running_stat = False
+
+    def load_act_ranges(self, ranges):
+        for k, (mn, mx) in ranges.items():
+            self.acts[k].x_min = torch.tensor([mn], dtype=torch.float32)
+            self.acts[k].x_max = torch.tensor([mx], dtype=torch.float32)
+
+    def _act(self, name, *args, **kw):
+        out = self.acts[name](*args, **kw)
+        if self.trace is not None:
+            self.trace[name] = torch.round(out[0] / out[1].view(-1)).to(torch.int64)
+        return out
+
+    def _unit(self, p, residual, x, sf32):
+        """Q_LinearBottleneck.forward q_mobilenetv2.py:58-93."""
+        identity = x
+        x, a_sf = self._act(p + ".quant_act", x, sf32)
+        x, w_sf = self.convs[p + ".conv1"](x, a_sf)
+        x = F.relu6(x)
+        x, a_sf = self._act(p + ".quant_act1", x, a_sf, w_sf)
+        x, w_sf = self.convs[p + ".conv2"](x, a_sf)
+        x = F.relu6(x)
+        x, a_sf = self._act(p + ".quant_act2", x, a_sf, w_sf)
+        x, w_sf = self.convs[p + ".conv3"](x, a_sf)
+        if residual:
+            x = x + identity
+            return self._act(p + ".quant_act_int32", x, a_sf, w_sf, identity, sf32, None)
+        return self._act(p + ".quant_act_int32", x, a_sf, w_sf)
+
+    @torch.no_grad()
+    def forward(self, x, trace=False):
+        """Q_MobileNetV2.forward q_mobilenetv2.py:182-212."""
+        self.trace = {} if trace else None
+        x, a_sf = self._act("quant_input", x)
+        x, w_sf = self.convs["init_block"](x, a_sf)
+        x = F.relu6(x)
+        x, a_sf = self._act("quant_act_int32", x, a_sf, w_sf)
+        for p, residual in self.units:
+            x, a_sf = self._unit(p, residual, x, a_sf)
+        x, a_sf = self._act("quant_act_before_final_block", x, a_sf)
+        x, w_sf = self.convs["features.final_block"](x, a_sf)
+        x = F.relu6(x)
+        x, a_sf = self._act("quant_act_int32_final", x, a_sf, w_sf)
+        x, a_sf = int_avgpool(x, a_sf, self.pool)
+        x, a_sf = self._act("quant_act_output", x, a_sf)
+        x, _ = self.out(x, a_sf)
+        return x.view(x.size(0), -1)
+
+    __call__ = forward
+
+    def harvest(self):
+        """Frozen integer parameters after a forward (layout of FakeQuantResNet.harvest, plus groups and the unit list)."""
+        convs = {}
+        for k, c in self.convs.items():
+            convs[k] = dict(weight_integer=c.weight_integer.clone(), bias_integer=c.bias_integer.clone(), w_sf=c.w_sf.clone(),
+                            stride=c.conv.stride[0], pad=c.conv.padding[0], groups=c.conv.groups)
+        acts = {k: dict(scale=a.scale.clone(), bits=a.bits, mode=a.mode) for k, a in self.acts.items()}
+        out = dict(weight_integer=self.out.weight_integer.clone(), w_sf=self.out.w_sf.clone(),
+                   bias_integer=None if self.out.bias_integer is None else self.out.bias_integer.clone())
+        return dict(arch="mobilenetv2_w1", convs=convs, acts=acts, output=out, units=list(self.units),
+                    pool=int(self.pool.kernel_size if isinstance(self.pool.kernel_size, int) else self.pool.kernel_size[0]))

@@ -226,3 +226,103 @@ class IntResNet:
         return acc.astype(np.float32) * scale                             # quant_modules.py:129-130
 
     __call__ = forward
+
+
+# ----------------------------------------------------------------------------- MobileNetV2 (integer semantics)
+def dwconv2d_nhwc(x, w, stride, pad):
+    """Depthwise convolution: x [N,H,W,C] ints, w [C,kh,kw,1] ints -> int64 [N,Ho,Wo,C]; exact via fp64 (asserted)."""
+    c = x.shape[3]
+    xt = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).permute(0, 3, 1, 2)
+    wt = torch.from_numpy(np.ascontiguousarray(np.asarray(w, dtype=np.float64))).permute(0, 3, 1, 2)
+    assert float(np.abs(np.asarray(x)).max(initial=0)) * float(np.abs(np.asarray(w)).sum(axis=(1, 2, 3)).max(initial=0)) < 2 ** 53
+    y = F.conv2d(xt, wt, None, stride, pad, 1, c)
+    return np.ascontiguousarray(y.permute(0, 2, 3, 1).numpy()).astype(I64)
+
+
+def relu6_cap(a_sf, w_sf):
+    """Accumulator value that ReLU6 turns every larger accumulator into.  The reference clamps the fp32 activation acc * (w_sf * a_sf)
+    at 6.0 (nn.ReLU6, q_mobilenetv2.py:68,72) and the QuantAct behind it recovers integers with round(z / a_sf / w_sf) in fp32
+    (quant_utils.py:392): a clamped value becomes C_c = round_f32(6 / a_sf / w_sf_c), an unclamped one its accumulator.  (C_c + 1)
+    * s > 6 and (C_c - 1) * s < 6 by more than fp32 rounding can bridge, so the composition is exactly min(acc, C_c) per channel -
+    and because the dyadic requantisation is monotone, ReLU6 is a per-channel upper clamp RHE(C_c * m_c / 2^e_c) of its output."""
+    six = np.float32(6.0)
+    return np.rint(six / np.float32(a_sf) / np.asarray(w_sf, dtype=np.float32)).astype(I64)
+
+
+class IntMobileNetV2:
+    """Integer-only MobileNetV2 from ``FakeQuantMobileNetV2.harvest()``: what a frozen engine has to compute (depthwise
+    convolutions, ReLU6 as the per-channel accumulator cap above, signed 16-bit residual stream without ReLU, unit input as the
+    case-1 identity, 1x1 QuantConv2d classifier).  Pinned to the reference by tests/test_mobilenetv2_cpu.py."""
+
+    def __init__(self, h):
+        self.h = h
+        self.convs = {}
+        for k, c in h["convs"].items():
+            w = c["weight_integer"].numpy().astype(I64).transpose(0, 2, 3, 1)
+            self.convs[k] = dict(w=np.ascontiguousarray(w), b=c["bias_integer"].numpy().astype(I64), w_sf=c["w_sf"].numpy().astype(np.float32),
+                                 stride=c["stride"], pad=c["pad"], groups=c["groups"])
+        self.acts = {k: dict(scale=np.float32(a["scale"].item()), bits=a["bits"], mode=a["mode"]) for k, a in h["acts"].items()}
+        o = h["output"]
+        self.out = dict(w=o["weight_integer"].numpy().astype(I64).reshape(o["weight_integer"].shape[0], -1),
+                        w_sf=o["w_sf"].numpy().astype(np.float32),
+                        b=None if o["bias_integer"] is None else o["bias_integer"].numpy().astype(I64))
+        self.trace = None
+
+    def _conv(self, name, x):
+        c = self.convs[name]
+        f = dwconv2d_nhwc if c["groups"] > 1 else conv2d_nhwc
+        return f(x, c["w"], c["stride"], c["pad"]) + c["b"]
+
+    def _case0(self, name, acc, a_sf, w_sf, relu6=False):
+        a = self.acts[name]
+        m, e = dyadic_vec(requant_ratio(a_sf, w_sf, a["scale"]))
+        if relu6:
+            acc = np.minimum(np.maximum(acc, 0), relu6_cap(a_sf, w_sf))
+        lo, hi = clamp_range(a["bits"], a["mode"])
+        q = np.clip(requant(acc, m, e), lo, hi)
+        if self.trace is not None:
+            self.trace[name] = q
+        return q
+
+    def _unit(self, p, residual, x16, s16):
+        a, one = self.acts, np.float32(1.0)
+        x = self._case0(p + ".quant_act", x16, s16, one)
+        s = a[p + ".quant_act"]["scale"]
+        for k in (1, 2):
+            conv = "%s.conv%d" % (p, k)
+            x = self._case0("%s.quant_act%d" % (p, k), self._conv(conv, x), s, self.convs[conv]["w_sf"], relu6=True)
+            s = a["%s.quant_act%d" % (p, k)]["scale"]
+        acc = self._conv(p + ".conv3", x)
+        out = a[p + ".quant_act_int32"]
+        if not residual:
+            return self._case0(p + ".quant_act_int32", acc, s, self.convs[p + ".conv3"]["w_sf"]), out["scale"]
+        m1, e1 = dyadic_vec(requant_ratio(s16, one, out["scale"]))                  # identity = the unit's 16-bit input
+        m2, e2 = dyadic_vec(requant_ratio(s, self.convs[p + ".conv3"]["w_sf"], out["scale"]))
+        y = requant(x16, m1, e1) + requant(acc, m2, e2)                              # case 1: no clamp, no ReLU (signed stream)
+        if self.trace is not None:
+            self.trace[p + ".quant_act_int32"] = y
+        return y, out["scale"]
+
+    def forward(self, x_nchw_f32, trace=False):
+        self.trace = {} if trace else None
+        a_in, one = self.acts["quant_input"], np.float32(1.0)
+        q = quantize_input(x_nchw_f32, a_in["scale"], a_in["bits"], a_in["mode"])
+        if self.trace is not None:
+            self.trace["quant_input"] = q
+        x16 = self._case0("quant_act_int32", self._conv("init_block", q), a_in["scale"], self.convs["init_block"]["w_sf"], relu6=True)
+        s16 = self.acts["quant_act_int32"]["scale"]
+        for p, residual in self.h["units"]:
+            x16, s16 = self._unit(p, residual, x16, s16)
+        x = self._case0("quant_act_before_final_block", x16, s16, one)
+        s = self.acts["quant_act_before_final_block"]["scale"]
+        x16 = self._case0("quant_act_int32_final", self._conv("features.final_block", x), s, self.convs["features.final_block"]["w_sf"], relu6=True)
+        s16 = self.acts["quant_act_int32_final"]["scale"]
+        pooled = avgpool_trunc(x16, self.h["pool"])
+        xo = self._case0("quant_act_output", pooled, s16, one)
+        s_o = self.acts["quant_act_output"]["scale"]
+        acc = linear(xo.reshape(xo.shape[0], -1), self.out["w"])
+        if self.out["b"] is not None:
+            acc = acc + self.out["b"]
+        return acc.astype(np.float32) * (self.out["w_sf"] * np.float32(s_o)).astype(np.float32)     # quant_modules.py:718,726-736
+
+    __call__ = forward

@@ -50,10 +50,11 @@ def load():
     import utils.quantization_utils.quant_modules as qm  # noqa
     import utils.quantization_utils.quant_utils as qu  # noqa
     import utils.models.q_resnet as qr  # noqa
+    import utils.models.q_mobilenetv2 as qmb  # noqa
     spec = importlib.util.spec_from_file_location("_ref_bit_config", os.path.join(REF_ROOT, "bit_config.py"))
     bc = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bc)
-    ns = types.SimpleNamespace(quant_modules=qm, quant_utils=qu, q_resnet=qr,
+    ns = types.SimpleNamespace(quant_modules=qm, quant_utils=qu, q_resnet=qr, q_mobilenetv2=qmb,
                                bit_config_dict=bc.bit_config_dict)
     _loaded["ns"] = ns
     return ns
@@ -100,6 +101,19 @@ def build_reference_qresnet(arch, scheme, float_model, calib):
     with torch.no_grad():
         q(calib)
     ns.quant_modules.freeze_model(q)
+    return q
+
+
+def build_reference_qmobilenetv2(scheme, float_model, calib, freeze=True):
+    """q_mobilenetv2_w1(float skeleton) -> stamp -> one calibration forward (running_stat) -> freeze (reference quant_train.py flow)."""
+    ns = load()
+    q = ns.q_mobilenetv2.q_mobilenetv2_w1(float_model)
+    stamp_like_quant_train(q, ns.bit_config_dict["bit_config_mobilenetv2_w1_%s" % scheme])
+    q.eval()
+    with torch.no_grad():
+        q(calib)
+    if freeze:
+        ns.quant_modules.freeze_model(q)
     return q
 
 

@@ -229,6 +229,38 @@ def make_net(ns, arch, scheme):
     print(arch, scheme, "ok", logits[0, :3].tolist())
 
 
+def make_net_mobilenetv2(ns, scheme):
+    """MobileNetV2-1.0 (reference utils/models/q_mobilenetv2.py) on the synthetic skeleton: frozen logits, every QuantAct's
+    integers, integer weights / biases of every convolution (depthwise ones included) and of the 1x1 classifier."""
+    from hawq_b200.synthetic import synthetic_float_mobilenetv2
+    qm = ns.quant_modules
+    net = synthetic_float_mobilenetv2(0)
+    calib = synthetic_batch(CALIB_BATCH, CALIB_SEED)
+    q = rh.build_reference_qmobilenetv2(scheme, net, calib)
+    x = synthetic_batch(PARITY_BATCH, PARITY_SEED)
+    logits, acts = rh.run_with_act_hooks(q, x)
+    out = {"logits": logits.numpy()}
+    meta = {"arch": "mobilenetv2_w1", "scheme": scheme, "calib": [CALIB_BATCH, CALIB_SEED], "input": [PARITY_BATCH, PARITY_SEED],
+            "acts": {}, "convs": {}, "torch": torch.__version__}
+    for name, mod in q.named_modules():
+        if type(mod) is qm.QuantAct:
+            a = nhwc(acts[name])
+            meta["acts"][name] = dict(x_min=float(mod.x_min), x_max=float(mod.x_max), scale=float(mod.act_scaling_factor),
+                                      bits=mod.activation_bit, mode=mod.quant_mode, shape=list(a.shape),
+                                      sha=sha_i32(a), sum=int(a.sum()), abssum=int(np.abs(a).sum()),
+                                      min=int(a.min()), max=int(a.max()))
+        elif type(mod) in (qm.QuantBnConv2d, qm.QuantConv2d):
+            w = mod.weight_integer.numpy().transpose(0, 2, 3, 1)      # OHWI (I = 1 for depthwise)
+            b = mod.bias_integer
+            sf = mod.convbn_scaling_factor if type(mod) is qm.QuantBnConv2d else mod.conv_scaling_factor
+            meta["convs"][name] = dict(w_sha=sha_i32(w), b_sha=sha_i32(b.numpy()) if b is not None else None,
+                                       w_bits=mod.weight_bit, shape=list(w.shape), groups=int(mod.conv.groups) if hasattr(mod, "conv") else 1,
+                                       sf_sha=hashlib.sha256(sf.numpy().tobytes()).hexdigest())
+    out["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, "net_mobilenetv2_w1_%s.npz" % scheme), **out)
+    print("mobilenetv2_w1", scheme, "ok", logits[0, :3].tolist())
+
+
 def make_kat_multibranch(ns):
     """The reference's un-frozen QuantAct on a (tensor, [scale per branch], [channels per branch]) input."""
     out = {}
@@ -253,6 +285,9 @@ if __name__ == "__main__":
     ns = rh.load()
     if len(sys.argv) == 2 and sys.argv[1] == "--multibranch":  # QuantAct on concatenated branches (quant_modules.py:275-286)
         make_kat_multibranch(ns)
+        sys.exit(0)
+    if len(sys.argv) == 3 and sys.argv[1] == "--mobilenetv2":  # e.g. --mobilenetv2 uniform8
+        make_net_mobilenetv2(ns, sys.argv[2])
         sys.exit(0)
     if len(sys.argv) == 4 and sys.argv[1] == "--net":         # one extra network golden, e.g. --net resnet101 uniform8
         make_net(ns, sys.argv[2], sys.argv[3])

@@ -41,3 +41,34 @@ def test_reference_graph_code_on_our_modules(monkeypatch, arch, scheme):
     with torch.no_grad():
         out = q(synthetic_batch(*meta["input"]))
     assert np.array_equal(out.numpy(), logits_g)
+
+
+def test_reference_mobilenetv2_graph_code_on_our_modules_unfrozen(monkeypatch):
+    """utils/models/q_mobilenetv2.py (Q_LinearBottleneck / Q_MobileNetV2: nn.ReLU6, depthwise QuantBnConv2d, `x + identity` without
+    ReLU, QuantConv2d classifier) built on this package's modules: the calibration forward gives the reference's ranges and the
+    same fp32 outputs as the reference's own modules.  (The frozen integer path of this family is not built: DESIGN.md row f3.)"""
+    import json
+    import os
+    from hawq_b200.synthetic import synthetic_float_mobilenetv2
+    ns = rh.load()
+    qmb = ns.q_mobilenetv2
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "net_mobilenetv2_w1_uniform8.npz"))
+    meta = json.loads(str(z["meta"]))
+    x = synthetic_batch(*meta["calib"])
+    ref = rh.build_reference_qmobilenetv2("uniform8", synthetic_float_mobilenetv2(0), x, freeze=False)     # reference modules
+    with torch.no_grad():
+        want = ref(synthetic_batch(*meta["input"]))          # second un-frozen forward (ranges keep moving, like ours below)
+    for name in ("QuantAct", "QuantBnConv2d", "QuantLinear", "QuantAveragePool2d", "QuantConv2d"):
+        monkeypatch.setattr(qmb, name, getattr(hb, name))
+    q = qmb.q_mobilenetv2_w1(synthetic_float_mobilenetv2(0))
+    assert type(q).__module__.startswith("utils.models") and isinstance(q.features.stage2.unit1.conv2, hb.QuantBnConv2d)
+    rh.stamp_like_quant_train(q, ns.bit_config_dict["bit_config_mobilenetv2_w1_uniform8"])
+    q.eval()
+    with torch.no_grad():
+        q(x)
+    for name, m in q.named_modules():
+        if isinstance(m, hb.QuantAct):
+            assert float(m.x_min) == meta["acts"][name]["x_min"] and float(m.x_max) == meta["acts"][name]["x_max"], name
+    with torch.no_grad():
+        got = q(synthetic_batch(*meta["input"]))
+    assert torch.equal(got, want)
