@@ -4,6 +4,7 @@ Public surface (mirrors the reference's module API for the quantized forward pat
   modules      QuantAct, QuantBnConv2d, QuantConv2d, QuantLinear, QuantAveragePool2d, QuantMaxPool2d, QuantDropout,
                freeze_model, unfreeze_model
   q_resnet     q_resnet18 / q_resnet50 / q_resnet101 (same module names / state_dict keys as the reference)
+  q_mobilenetv2  q_mobilenetv2_w1: graph and un-frozen arithmetic only (no frozen integer path yet)
   bit_config   bit_config_dict(), get_bit_config(arch, scheme), stamp_bit_config(model, cfg)
   engine       compile_model(model, example) -> CompiledModel (one CUDA graph per GPU), all_gather_logits
   ops / _lib   the C ABI (include/hawq_b200.h) through ctypes
@@ -13,11 +14,14 @@ from .modules import (QuantAct, QuantAveragePool2d, QuantBnConv2d, QuantConv2d, 
                       QuantMaxPool2d, freeze_model, unfreeze_model)
 from .q_resnet import (Q_ResBlockBn, Q_ResNet18, Q_ResNet50, Q_ResNet101, Q_ResUnitBn, q_resnet18, q_resnet50,  # noqa: F401
                        q_resnet101, quantize_arch_dict)
+from .q_mobilenetv2 import Q_LinearBottleneck, Q_MobileNetV2, q_mobilenetv2_w1  # noqa: F401
 from .bit_config import bit_config_dict, get_bit_config, stamp_bit_config  # noqa: F401
 from .engine import CompiledModel, all_gather_logits, compile_model, shard_range  # noqa: F401
 from .qtensor import IntActivation  # noqa: F401
 from .checkpoint import (apply_integer_checkpoint, export_tvm_params, load_quantized_checkpoint,  # noqa: F401
                          quantized_checkpoint_dict, save_quantized_checkpoint, save_tvm_params)
+
+quantize_arch_dict = dict(quantize_arch_dict, mobilenetv2_w1=q_mobilenetv2_w1)      # reference quant_train.py:150-158
 
 __version__ = "0.1.0"
 
