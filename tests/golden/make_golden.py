@@ -6,6 +6,7 @@ Outputs (small, committed):
   kat_modules.npz      QuantAct(input) / QuantBnConv2d / QuantConv2d / QuantLinear / QuantAveragePool2d on tiny shapes
   net_<arch>_<scheme>.npz   whole-network: act ranges, per-QuantAct checksums of the activation integers,
                             per-layer checksums of weight_integer / bias_integer, logits  (batch 2)
+  net_mobilenetv2_w1_<scheme>.npz   the same for MobileNetV2-1.0 (python tests/golden/make_golden.py --mobilenetv2 uniform8|uniform4)
 Nothing here runs on the GPU box; tests only read the .npz files.
 """
 import hashlib
