@@ -326,3 +326,18 @@ class IntMobileNetV2:
         return acc.astype(np.float32) * (self.out["w_sf"] * np.float32(s_o)).astype(np.float32)     # quant_modules.py:718,726-736
 
     __call__ = forward
+
+
+def multibranch_requant(x_int, branch_scales, branch_channels, new_scale, bits, mode):
+    """QuantAct on a channel-concatenation of branches with different scales (quant_modules.py:275-286, the InceptionV3 edges):
+    every branch is requantised on its own with case 0 and weight scale s_i / s_i = 1: q = clamp(RHE(x_i * m_i / 2^e_i)) with
+    (m_i, e_i) = batch_frexp(s_i / new_scale).  x_int: NHWC integers of the concatenation.  In an integer engine this is one
+    per-channel requantisation (hawq_requant with chan[c] = (0, m_branch(c), e_branch(c)))."""
+    out = np.empty_like(np.asarray(x_int, dtype=I64))
+    lo, hi = clamp_range(bits, mode)
+    c0 = 0
+    for s, c in zip(branch_scales, branch_channels):
+        m, e = dyadic_vec(requant_ratio(np.float32(s), np.float32(1.0), np.float32(new_scale)))
+        out[..., c0:c0 + c] = np.clip(requant(np.asarray(x_int, dtype=I64)[..., c0:c0 + c], m, e), lo, hi)
+        c0 += c
+    return out
